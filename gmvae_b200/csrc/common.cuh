@@ -1,0 +1,112 @@
+// common.cuh -- shared device helpers: numerics, reductions, Philox, error plumbing.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace gmvae {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------- host errors
+void set_error(const std::string& msg);
+#define GM_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::gmvae::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                         ":" + std::to_string(__LINE__) + ")");                              \
+      return -2;                                                                             \
+    }                                                                                        \
+  } while (0)
+#define GM_REQUIRE(cond, msg)                   \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::gmvae::set_error(std::string(msg));     \
+      return -1;                                \
+    }                                           \
+  } while (0)
+#define GM_TRY(expr)           \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+// ----------------------------------------------------------------------------- conversions
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// ----------------------------------------------------------------------------- numerics (fp32)
+// log(1+e^t), the same asymptote handling as tf.nn.softplus / torch.logaddexp(t,0).
+__device__ __forceinline__ float softplus_f(float t) { return fmaxf(t, 0.f) + log1pf(expf(-fabsf(t))); }
+__device__ __forceinline__ float sigmoid_f(float t) {
+  // stable for both signs
+  float e = expf(-fabsf(t));
+  float s = 1.f / (1.f + e);
+  return t >= 0.f ? s : e * s;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the block, result valid in thread 0. `scratch` >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? scratch[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  __device__ static __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  // 4 random words for (seed, stream, counter)
+  __device__ static __forceinline__ void gen(uint64_t seed, uint64_t stream, uint64_t ctr, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(c, k0, k1);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+// uniform in (0,1): never 0, never 1
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+}  // namespace gmvae

@@ -1,0 +1,864 @@
+// engine.cu -- the GMVAE / VAE / VAE_GMP training step on B200 and its C ABI (include/gmvae_abi.h).
+//
+// One iteration of the reference's hot loop `sess.run([train_op, global_step])`
+// (/root/reference/scripts/runners.py:231-232) = forward (gmvae.py:238-267 / vae.py:167-185)
+// + reverse-mode gradients of every trainable variable (runners.py:182) + TF-form Adam
+// (runners.py:183), expressed as a fixed sequence of kernels on the caller's stream.
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/gmvae_abi.h"
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace gmvae {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+// ============================================================================ TMA descriptors
+namespace tc {
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
+                   uint32_t box_inner, uint32_t box_outer) {
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> Key;
+  static thread_local std::map<Key, CUtensorMap> cache;
+  Key key(ptr, inner, outer, outer_stride, box_inner, box_outer);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  EncodeTiledFn fn = get_encode_fn();
+  GM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  GM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base must be 16-byte aligned");
+  GM_REQUIRE((outer_stride * 2) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {outer_stride * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -3;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+}  // namespace tc
+
+// ============================================================================ model description
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Linear {
+  int in = 0, out = 0;
+  int64_t w_off = 0, b_off = 0;
+  bf16* w_bf16 = nullptr;  int ld_w = 0;    // [in, ld_w]
+  bf16* wt_bf16 = nullptr; int ld_wt = 0;   // [out, ld_wt]
+};
+struct Mlp {
+  std::string name;
+  std::vector<Linear> layers;
+};
+
+// A (sub-)matrix of a Linear: rows [row0, row0+in) of W.
+struct LinView {
+  const float* w; float* dw; const float* b; float* db;
+  int in, out, ldw32;               // fp32 row stride (= full `out`)
+  const bf16* w_bf16; int ld_w;     // [in, ld_w]
+  const bf16* wt_bf16; int ld_wt;   // [out, ld_wt], already offset to column row0
+};
+
+enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8 };
+
+}  // namespace gmvae
+
+using namespace gmvae;
+
+struct gmvae_handle {
+  gmvae_config cfg;
+  int D, Z, K, L;                      // L = layers per MLP = num_hidden + 1
+  std::vector<int> hidden;
+  std::vector<gmvae_param_desc> table;
+  int64_t n_params = 0;                // padded flat count
+  Mlp prior_gmm, decoder, encoder_y, encoder;   // `encoder` = encoder (VAE) / encoder_gmm (GMVAE)
+  int64_t loc_off = -1, raw_scale_off = -1, mix_off = -1;
+  // bound buffers
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  uint8_t* ws = nullptr; size_t ws_bytes = 0;
+  // workspace carve-outs (bytes offsets resolved at bind)
+  struct Buf { size_t off = 0, bytes = 0; };
+  std::map<std::string, Buf> bufs;
+  size_t ws_needed = 0;
+  std::vector<ShadowEntry> shadow_host;
+  ShadowEntry* shadow_dev = nullptr; int shadow_tiles = 0;
+  DeviceState* state = nullptr;
+  int64_t launches = 0;
+  int debug_flags = 0;
+  // NCCL
+  ncclComm_t comm = nullptr; int world = 1, rank = 0;
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+
+  bool bf16_mode() const { return cfg.precision == GMVAE_PRECISION_BF16; }
+  size_t act_size() const { return bf16_mode() ? 2 : 4; }
+  template <typename T> T* buf(const std::string& name) const {
+    auto it = bufs.find(name);
+    return it == bufs.end() ? nullptr : reinterpret_cast<T*>(ws + it->second.off);
+  }
+};
+
+namespace gmvae {
+
+static void add_param(gmvae_handle* h, const std::string& name, int rows, int cols, int64_t* off_out) {
+  gmvae_param_desc d;
+  memset(&d, 0, sizeof(d));
+  snprintf(d.name, GMVAE_NAME_LEN, "%s", name.c_str());
+  d.offset = h->n_params; d.rows = rows; d.cols = cols;
+  h->table.push_back(d);
+  if (off_out) *off_out = h->n_params;
+  h->n_params += round_up(rows * cols, 4);   // keep every tensor 16-byte aligned
+}
+
+static void build_mlp(gmvae_handle* h, Mlp& m, const std::string& name, int in, const std::vector<int>& sizes) {
+  m.name = name;
+  int prev = in;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    Linear l; l.in = prev; l.out = sizes[i];
+    add_param(h, name + "_fcnet/linear_" + std::to_string(i) + "/w", l.in, l.out, &l.w_off);
+    add_param(h, name + "_fcnet/linear_" + std::to_string(i) + "/b", 1, l.out, &l.b_off);
+    m.layers.push_back(l);
+    prev = sizes[i];
+  }
+}
+
+static void plan_buf(gmvae_handle* h, const std::string& name, size_t bytes) {
+  gmvae_handle::Buf b; b.off = h->ws_needed; b.bytes = bytes;
+  h->bufs[name] = b;
+  h->ws_needed += (bytes + 255) / 256 * 256;
+}
+
+static void plan_mlp_bufs(gmvae_handle* h, const Mlp& m, size_t B, size_t asz) {
+  for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
+    plan_buf(h, m.name + ".h" + std::to_string(i), B * m.layers[i].out * asz);
+    plan_buf(h, m.name + ".dh" + std::to_string(i), B * m.layers[i].out * asz);
+  }
+}
+
+static void plan_shadows(gmvae_handle* h, Mlp& m) {
+  for (auto& l : m.layers) {
+    l.ld_w = round_up(l.out, 8); l.ld_wt = round_up(l.in, 8);
+    plan_buf(h, "shadow.w." + std::to_string(l.w_off), (size_t)l.in * l.ld_w * 2);
+    plan_buf(h, "shadow.wt." + std::to_string(l.w_off), (size_t)l.out * l.ld_wt * 2);
+  }
+}
+
+static int plan(gmvae_handle* h) {
+  const gmvae_config& c = h->cfg;
+  h->D = c.data_size; h->Z = c.latent_size; h->K = c.model == GMVAE_MODEL_VAE ? 1 : c.mixture_components;
+  h->hidden.assign(c.hidden_sizes, c.hidden_sizes + c.num_hidden);
+  h->L = c.num_hidden + 1;
+  const int D = h->D, Z = h->Z, K = h->K;
+  auto with = [&](int last) { std::vector<int> v = h->hidden; v.push_back(last); return v; };
+  // Variable order = graph-construction order of the reference factories.
+  if (c.model == GMVAE_MODEL_GMVAE) {                       // gmvae.py:321-353
+    build_mlp(h, h->prior_gmm, "prior_gmm", K, std::vector<int>{2 * Z});
+    build_mlp(h, h->decoder, "decoder", Z, with(D));
+    build_mlp(h, h->encoder_y, "encoder_y", D, with(K));
+    build_mlp(h, h->encoder, "encoder_gmm", D + K, with(2 * Z));
+  } else {                                                  // vae.py:231-268
+    if (c.model == GMVAE_MODEL_VAE_GMP) {
+      add_param(h, "loc", K, Z, &h->loc_off);
+      add_param(h, "raw_scale_diag", K, Z, &h->raw_scale_off);
+      add_param(h, "mixture_logits", 1, K, &h->mix_off);
+    }
+    build_mlp(h, h->decoder, "decoder", Z, with(D));
+    build_mlp(h, h->encoder, "encoder", D, with(2 * Z));
+  }
+  // ---- workspace ----
+  const size_t B = (size_t)c.max_batch, asz = h->act_size();
+  const int Kp = round_up(K, 8);
+  plan_buf(h, "x_act", B * D * asz);
+  plan_buf(h, "eps", B * Z * 4);
+  plan_buf(h, "dec.dlogits", B * D * asz);
+  plan_buf(h, "dz", B * Z * 4);
+  plan_buf(h, "enc_out", B * 2 * Z * 4);
+  plan_buf(h, "d_enc_out", B * 2 * Z * asz);
+  plan_buf(h, "z_act", B * Z * asz);
+  plan_mlp_bufs(h, h->decoder, B, asz);
+  plan_mlp_bufs(h, h->encoder, B, asz);
+  if (c.model == GMVAE_MODEL_GMVAE) {
+    plan_mlp_bufs(h, h->encoder_y, B, asz);
+    plan_buf(h, "u", B * K * 4);
+    plan_buf(h, "logits_y", B * K * 4);
+    plan_buf(h, "y_f32", B * K * 4);
+    plan_buf(h, "y_act", B * Kp * asz);
+    plan_buf(h, "prior_out", B * 2 * Z * 4);
+    plan_buf(h, "d_prior_out", B * 2 * Z * 4);
+    plan_buf(h, "dy", B * K * 4);
+    plan_buf(h, "dlogits_y", B * K * 4);
+    plan_buf(h, "pre_y", B * (size_t)(h->hidden.empty() ? 2 * Z : h->hidden[0]) * 4);
+  }
+  if (c.model == GMVAE_MODEL_VAE_GMP) {
+    plan_buf(h, "z_f32", B * Z * 4);
+    plan_buf(h, "dz_prior", B * Z * 4);
+  }
+  if (h->bf16_mode()) {
+    plan_shadows(h, h->decoder); plan_shadows(h, h->encoder);
+    if (c.model == GMVAE_MODEL_GMVAE) { plan_shadows(h, h->encoder_y); plan_shadows(h, h->prior_gmm); }
+  }
+  plan_buf(h, "dbg.a", 16); plan_buf(h, "dbg.b", 16);  // placeholders
+  return 0;
+}
+
+static LinView view(const gmvae_handle* h, const Linear& l, int row0 = 0, int rows = -1) {
+  if (rows < 0) rows = l.in - row0;
+  LinView v;
+  v.w = h->params + l.w_off + (int64_t)row0 * l.out;
+  v.dw = h->grads + l.w_off + (int64_t)row0 * l.out;
+  v.b = h->params + l.b_off; v.db = h->grads + l.b_off;
+  v.in = rows; v.out = l.out; v.ldw32 = l.out;
+  v.w_bf16 = l.w_bf16 ? l.w_bf16 + (int64_t)row0 * l.ld_w : nullptr; v.ld_w = l.ld_w;
+  v.wt_bf16 = l.wt_bf16 ? l.wt_bf16 + row0 : nullptr; v.ld_wt = l.ld_wt;
+  return v;
+}
+
+// ============================================================================ GEMM dispatch
+#define GM_LAUNCHED(h, st)                                                   \
+  do {                                                                       \
+    (h)->launches++;                                                         \
+    if ((h)->debug_flags & DBG_SYNC_EACH) GM_CHECK_CUDA(cudaStreamSynchronize(st)); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <class Epi>
+static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Operand& B, const tc::Operand* A2,
+                          const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
+  int r;
+  if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else if (N % 128 != 0 && N % 112 == 0) r = tc::launch_gemm_tc<112, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  if (r == 0) GM_LAUNCHED(h, st);
+  return r;
+}
+
+// C[M,out] = A[M,in] * W (+ A2[M,in2] * W2)        forward through a linear layer
+template <typename TA, class Epi>
+static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinView& L, const Epi& epi, cudaStream_t st,
+                   const TA* A2 = nullptr, int64_t lda2 = 0, const LinView* L2 = nullptr) {
+  if constexpr (std::is_same<TA, bf16>::value) {
+    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && L.in >= 32 && L.out >= 32 && lda % 8 == 0 &&
+              aligned16(A) && aligned16(L.wt_bf16);
+    if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->wt_bf16);
+    if (ok) {
+      tc::Operand a{A, lda, M, L.in}, b{L.wt_bf16, L.ld_wt, L.out, L.in};
+      if (L2) {
+        tc::Operand a2{A2, lda2, M, L2->in}, b2{L2->wt_bf16, L2->ld_wt, L2->out, L2->in};
+        return tc_dispatch_kk(h, a, b, &a2, &b2, M, L.out, epi, st);
+      }
+      return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.out, epi, st);
+    }
+  }
+  GM_REQUIRE(L2 == nullptr, "two-segment forward requires the tensor-core path");
+  GM_CHECK_CUDA((launch_gemm_simt<TA, float, Epi>(A, lda, 1, L.w, L.ldw32, 1, M, L.out, L.in, 1, epi, st)));
+  GM_LAUNCHED(h, st);
+  return 0;
+}
+
+// dX[M,in] = dY[M,out] * W^T
+template <typename TD, class Epi>
+static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const LinView& L, const Epi& epi, cudaStream_t st) {
+  if constexpr (std::is_same<TD, bf16>::value) {
+    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && L.in >= 32 && L.out >= 32 && ldy % 8 == 0 &&
+              aligned16(dY) && aligned16(L.w_bf16);
+    if (ok) {
+      tc::Operand a{dY, ldy, M, L.out}, b{L.w_bf16, L.ld_w, L.in, L.out};
+      return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.in, epi, st);
+    }
+  }
+  GM_CHECK_CUDA((launch_gemm_simt<TD, float, Epi>(dY, ldy, 1, L.w, 1, L.ldw32, M, L.in, L.out, 1, epi, st)));
+  GM_LAUNCHED(h, st);
+  return 0;
+}
+
+// dW[in,out] += A^T[in,M] * dY[M,out]   (grads pre-zeroed; split over the batch, fp32 atomics)
+template <typename TA, typename TD>
+static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, int64_t ldy, int M, const LinView& L,
+                     cudaStream_t st) {
+  EpiAtomicAdd epi{L.dw, (int64_t)L.ldw32};
+  if constexpr (std::is_same<TA, bf16>::value && std::is_same<TD, bf16>::value) {
+    bool ok = h->bf16_mode() && !(h->debug_flags & (DBG_NO_TC | DBG_NO_TC_WGRAD)) && L.in >= 32 && L.out >= 32 && lda % 8 == 0 &&
+              ldy % 8 == 0 && aligned16(A) && aligned16(dY);
+    if (ok) {
+      tc::Operand a{A, lda, L.in, M}, b{dY, ldy, L.out, M};
+      const int bn = L.out <= 64 ? 64 : 128;
+      const int tiles = ((L.in + 127) / 128) * ((L.out + bn - 1) / bn);
+      const int kb = (M + tc::BLOCK_K - 1) / tc::BLOCK_K;
+      int split = std::max(1, std::min(kb, (2 * 148 + tiles - 1) / tiles));
+      int r = bn == 64 ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
+                       : tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st);
+      if (r == 0) GM_LAUNCHED(h, st);
+      return r;
+    }
+  }
+  const int tiles = ((L.in + SIMT_BM - 1) / SIMT_BM) * ((L.out + SIMT_BN - 1) / SIMT_BN);
+  int split = std::max(1, std::min((M + 255) / 256, (4 * 148 + tiles - 1) / tiles));
+  GM_CHECK_CUDA((launch_gemm_simt<TA, TD, EpiAtomicAdd>(A, 1, lda, dY, ldy, 1, L.in, L.out, M, split, epi, st)));
+  GM_LAUNCHED(h, st);
+  return 0;
+}
+
+template <typename T>
+static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, float* db, cudaStream_t st) {
+  int rows_per_block = std::max(64, (M + 147) / 148);
+  rows_per_block = round_up(rows_per_block, 8);
+  dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<T><<<grid, 256, 0, st>>>(dY, ldy, M, N, rows_per_block, db);
+  GM_CHECK_CUDA(cudaGetLastError());
+  GM_LAUNCHED(h, st);
+  return 0;
+}
+
+// ============================================================================ MLP passes
+template <typename A> struct MlpBufs { std::vector<A*> hid, dhid; };
+
+template <typename A>
+static MlpBufs<A> mlp_bufs(const gmvae_handle* h, const Mlp& m) {
+  MlpBufs<A> b;
+  for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
+    b.hid.push_back(h->buf<A>(m.name + ".h" + std::to_string(i)));
+    b.dhid.push_back(h->buf<A>(m.name + ".dh" + std::to_string(i)));
+  }
+  return b;
+}
+
+// Hidden layers i >= first of an MLP: h[i] = relu(h[i-1] W_i + b_i). Layer 0's input is `in0`.
+template <typename A>
+static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int M, int first,
+                          cudaStream_t st) {
+  const int nh = (int)m.layers.size() - 1;
+  for (int i = first; i < nh; ++i) {
+    const A* in = i == 0 ? in0 : b.hid[i - 1];
+    int64_t ld = i == 0 ? ld0 : m.layers[i - 1].out;
+    LinView L = view(h, m.layers[i], 0, i == 0 ? (int)std::min<int64_t>(m.layers[0].in, ld0) : -1);
+    EpiStore<A> epi{b.hid[i], (int64_t)m.layers[i].out, L.b, nullptr, 0, 1, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, in, ld, M, L, epi, st));
+  }
+  return 0;
+}
+
+// Backward through the whole MLP given dOut = d loss / d (last layer output).
+// Computes every dW, db and the hidden gradients down to dh[0]; the gradient w.r.t. the MLP
+// input is left to the caller (it is only needed for z and y, never for the image x).
+// `in0_cols` = how many leading rows of W_0 multiply `in0` (encoder_gmm: D of D+K).
+template <typename A, typename TD>
+static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols,
+                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st) {
+  const int nl = (int)m.layers.size();
+  // last layer
+  {
+    const Linear& l = m.layers[nl - 1];
+    const bool first = nl == 1;
+    LinView L = view(h, l, 0, first ? in0_cols : -1);
+    const A* in = first ? in0 : b.hid[nl - 2];
+    int64_t ld = first ? ld0 : m.layers[nl - 2].out;
+    GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
+    GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
+    if (!first) {
+      EpiReluMask<A, A> epi{b.dhid[nl - 2], (int64_t)m.layers[nl - 2].out, b.hid[nl - 2], (int64_t)m.layers[nl - 2].out};
+      GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, view(h, l), epi, st)));
+    }
+  }
+  for (int i = nl - 2; i >= 0; --i) {
+    const Linear& l = m.layers[i];
+    const bool first = i == 0;
+    LinView L = view(h, l, 0, first ? in0_cols : -1);
+    const A* in = first ? in0 : b.hid[i - 1];
+    int64_t ld = first ? ld0 : m.layers[i - 1].out;
+    GM_TRY((lin_wgrad<A, A>(h, in, ld, b.dhid[i], l.out, M, L, st)));
+    GM_TRY(bias_grad<A>(h, b.dhid[i], l.out, M, l.out, L.db, st));
+    if (!first) {
+      EpiReluMask<A, A> epi{b.dhid[i - 1], (int64_t)m.layers[i - 1].out, b.hid[i - 1], (int64_t)m.layers[i - 1].out};
+      GM_TRY((lin_dgrad<A>(h, b.dhid[i], l.out, M, view(h, l), epi, st)));
+    }
+  }
+  return 0;
+}
+
+// ============================================================================ the step
+template <typename A>
+static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
+                                 const float* u_in, cudaStream_t st) {
+  const gmvae_config& c = h->cfg;
+  const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
+  const float inv_bg = 1.f / (float)Bg;
+  const bool gm = c.model == GMVAE_MODEL_GMVAE;
+  float* acc = h->grads + h->n_params;
+  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+
+  A* x_act = h->buf<A>("x_act");
+  {
+    int64_t n = (int64_t)B * D;
+    convert_x_kernel<A><<<(unsigned)((n / 16 + 255) / 256 + 1), 256, 0, st>>>(x_u8, x_act, n);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  }
+  const float* eps = eps_in; const float* u = u_in;
+  if (!eps || (gm && !u)) {
+    float* e = h->buf<float>("eps"); float* uu = gm ? h->buf<float>("u") : nullptr;
+    int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
+    int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
+    fill_noise_kernel<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(e, ne, uu, nu, h->state, (uint64_t)h->rank);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    if (!eps) eps = e;
+    if (gm && !u) u = uu;
+  }
+
+  MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder), enc = mlp_bufs<A>(h, h->encoder);
+  float* enc_out = h->buf<float>("enc_out");
+  A* d_enc_out = h->buf<A>("d_enc_out");
+  A* z_act = h->buf<A>("z_act");
+  float* dz = h->buf<float>("dz");
+  A* dlogits_x = h->buf<A>("dec.dlogits");
+  const int Kp = round_up(K, 8);
+  const Linear& enc_l0 = h->encoder.layers[0];
+  const Linear& enc_last = h->encoder.layers[nl - 1];
+
+  // -------------------------------------------------------------------------- forward
+  MlpBufs<A> ey; float *logits_y = nullptr, *y_f32 = nullptr, *prior_out = nullptr; A* y_act = nullptr;
+  bool two_seg = false;
+  if (gm) {
+    ey = mlp_bufs<A>(h, h->encoder_y);
+    logits_y = h->buf<float>("logits_y"); y_f32 = h->buf<float>("y_f32"); y_act = h->buf<A>("y_act");
+    prior_out = h->buf<float>("prior_out");
+    // q(y|x): encoder_y MLP, logits in fp32 (gmvae.py:238)
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, D, B, 0, st));
+    {
+      const Linear& l = h->encoder_y.layers[nl - 1];
+      EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 0, 1.f};
+      GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? D : h->hidden[nl - 2], B, view(h, l), epi, st));
+    }
+    head_y_fwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, u, B, K, 1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
+    {
+      const Linear& l = h->prior_gmm.layers[0];
+      EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 0, 1.f};
+      GM_TRY(lin_fwd<float>(h, y_f32, K, B, view(h, l), epi, st));
+    }
+    // q(z|x,y) layer 0: [x,y] W = x W[:D] + y W[D:]  (no concat, base.py:66)
+    LinView Lx = view(h, enc_l0, 0, D), Ly = view(h, enc_l0, D, K);
+    const bool last0 = nl == 1;
+    two_seg = std::is_same<A, bf16>::value && h->bf16_mode() && !(h->debug_flags & (DBG_NO_TC | DBG_NO_TWO_SEG)) && D % 8 == 0 &&
+              D >= 32 && enc_l0.out >= 32;
+    if (two_seg) {
+      if (last0) {
+        EpiStore<float> epi{enc_out, (int64_t)2 * Z, Lx.b, nullptr, 0, 0, 0, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st, y_act, Kp, &Ly));
+      } else {
+        EpiStore<A> epi{enc.hid[0], (int64_t)enc_l0.out, Lx.b, nullptr, 0, 1, 0, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st, y_act, Kp, &Ly));
+      }
+    } else {
+      float* pre = h->buf<float>("pre_y");
+      EpiStore<float> e0{pre, (int64_t)enc_l0.out, Lx.b, nullptr, 0, 0, 0, 1.f};
+      GM_TRY(lin_fwd<float>(h, y_f32, K, B, Ly, e0, st));
+      if (last0) {
+        EpiStore<float> epi{enc_out, (int64_t)2 * Z, nullptr, pre, (int64_t)enc_l0.out, 0, 0, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st));
+      } else {
+        EpiStore<A> epi{enc.hid[0], (int64_t)enc_l0.out, nullptr, pre, (int64_t)enc_l0.out, 1, 0, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st));
+      }
+    }
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, D, B, 1, st));
+  } else {
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, D, B, 0, st));
+  }
+  if (nl > 1 || !gm) {   // last encoder layer -> enc_out (fp32)
+    EpiStore<float> epi{enc_out, (int64_t)2 * Z, h->params + enc_last.b_off, nullptr, 0, 0, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : enc.hid[nl - 2], nl == 1 ? D : h->hidden[nl - 2], B, view(h, enc_last, 0, nl == 1 ? D : -1),
+                      epi, st));
+  }
+  // z head
+  const int prior_mode = gm ? 2 : (c.model == GMVAE_MODEL_VAE_GMP ? 1 : 0);
+  float* z_f32 = h->buf<float>("z_f32");
+  {
+    int64_t n = (int64_t)B * Z;
+    head_z_fwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, prior_mode, B, Z, c.raw_sigma_bias,
+                                                                    c.sigma_min, inv_bg, z_act, z_f32, acc);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  }
+  float* dz_prior = h->buf<float>("dz_prior");
+  if (prior_mode == 1) {
+    const int warps = 4;
+    gmp_prior_kernel<<<(B + warps - 1) / warps, warps * 32, warps * K * sizeof(float), st>>>(
+        z_f32, h->params + h->loc_off, h->params + h->raw_scale_off, h->params + h->mix_off, B, K, Z, inv_bg, dz_prior,
+        h->grads + h->loc_off, h->grads + h->raw_scale_off, h->grads + h->mix_off, acc);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  }
+  // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood
+  GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Z, B, 0, st));
+  {
+    const Linear& l = h->decoder.layers[nl - 1];
+    EpiBCE<A> epi{dlogits_x, (int64_t)D, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, nullptr,
+                  acc + ACC_NLL, inv_bg, 0.f};
+    GM_TRY(lin_fwd<A>(h, nl == 1 ? z_act : dec.hid[nl - 2], nl == 1 ? Z : h->hidden[nl - 2], B, view(h, l), epi, st));
+  }
+
+  // -------------------------------------------------------------------------- backward
+  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Z, Z, dlogits_x, D, B, st)));
+  {  // dz = d(first decoder layer input)
+    const Linear& l0 = h->decoder.layers[0];
+    EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 0, 1.f};
+    if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, D, B, view(h, l0), epi, st)));
+    else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], l0.out, B, view(h, l0), epi, st)));
+  }
+  float* d_prior_out = h->buf<float>("d_prior_out");
+  {
+    int64_t n = (int64_t)B * Z;
+    head_z_bwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, dz, dz_prior, prior_mode, B, Z,
+                                                                    c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, d_prior_out);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  }
+  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, D, D, d_enc_out, 2 * Z, B, st)));
+  if (gm) {
+    float* dy = h->buf<float>("dy"); float* dlogits_y = h->buf<float>("dlogits_y");
+    LinView Ly = view(h, enc_l0, D, K);
+    // y-columns of encoder_gmm layer 0: dW[D:] = y^T dh0 ; dy = dh0 W[D:]^T
+    if (nl == 1) {
+      GM_TRY((lin_wgrad<float, A>(h, y_f32, K, d_enc_out, 2 * Z, B, Ly, st)));
+      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
+      GM_TRY((lin_dgrad<A>(h, d_enc_out, 2 * Z, B, Ly, e, st)));
+    } else {
+      GM_TRY((lin_wgrad<float, A>(h, y_f32, K, enc.dhid[0], enc_l0.out, B, Ly, st)));
+      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
+      GM_TRY((lin_dgrad<A>(h, enc.dhid[0], enc_l0.out, B, Ly, e, st)));
+    }
+    // prior_gmm: dWp = y^T d_prior_out ; dbp ; dy += d_prior_out Wp^T
+    {
+      const Linear& l = h->prior_gmm.layers[0];
+      LinView Lp = view(h, l);
+      GM_TRY((lin_wgrad<float, float>(h, y_f32, K, d_prior_out, 2 * Z, B, Lp, st)));
+      GM_TRY(bias_grad<float>(h, d_prior_out, 2 * Z, B, 2 * Z, Lp.db, st));
+      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1, 1.f};
+      GM_TRY((lin_dgrad<float>(h, d_prior_out, 2 * Z, B, Lp, e, st)));
+    }
+    head_y_bwd_kernel<0><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_TRY((mlp_backward<A, float>(h, h->encoder_y, ey, x_act, D, D, dlogits_y, K, B, st)));
+  }
+  return 0;
+}
+
+static int refresh_shadows(gmvae_handle* h, bool bump, cudaStream_t st) {
+  if (h->shadow_tiles > 0) {
+    refresh_shadows_kernel<<<h->shadow_tiles, dim3(32, 8), 0, st>>>(h->shadow_dev, (int)h->shadow_host.size(), h->state, bump ? 1 : 0);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  } else if (bump) {
+    bump_step_kernel<<<1, 1, 0, st>>>(h->state);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  }
+  return 0;
+}
+
+static int check_ready(const gmvae_handle* h) {
+  GM_REQUIRE(h != nullptr, "null handle");
+  GM_REQUIRE(h->params != nullptr, "gmvae_bind has not been called");
+  return 0;
+}
+
+}  // namespace gmvae
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* gmvae_last_error(void) { return g_last_error.c_str(); }
+const char* gmvae_build_info(void) { return "gmvae_b200 sm_100a (tcgen05/TMA bf16 + fp32 SIMT validation) abi=1 " __DATE__ " " __TIME__; }
+
+int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
+  GM_REQUIRE(cfg && out, "null argument");
+  GM_REQUIRE(cfg->abi_version == GMVAE_ABI_VERSION, "ABI version mismatch");
+  GM_REQUIRE(cfg->model >= 0 && cfg->model <= 2, "unknown model");
+  GM_REQUIRE(cfg->precision == GMVAE_PRECISION_FP32 || cfg->precision == GMVAE_PRECISION_BF16, "unknown precision");
+  GM_REQUIRE(cfg->num_hidden >= 0 && cfg->num_hidden <= GMVAE_MAX_HIDDEN_LAYERS, "num_hidden out of range");
+  GM_REQUIRE(cfg->data_size > 0 && cfg->latent_size > 0 && cfg->max_batch > 0, "sizes must be positive");
+  for (int i = 0; i < cfg->num_hidden; ++i) GM_REQUIRE(cfg->hidden_sizes[i] > 0, "hidden sizes must be positive");
+  if (cfg->model != GMVAE_MODEL_VAE)
+    GM_REQUIRE(cfg->mixture_components >= 1 && cfg->mixture_components <= HEAD_MAXK, "mixture_components must be in [1,128]");
+  GM_REQUIRE(cfg->objective == GMVAE_OBJECTIVE_REFERENCE || cfg->model == GMVAE_MODEL_GMVAE, "objective applies to GMVAE only");
+  GM_REQUIRE(cfg->objective == GMVAE_OBJECTIVE_REFERENCE, "objective=marginal is not built yet");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libgmvae_b200 has no CPU fallback");
+    return -4;
+  }
+  GM_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device ordinal out of range");
+  cudaDeviceProp prop;
+  GM_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  GM_REQUIRE(prop.major == 10, "libgmvae_b200 is built for sm_100a (B200) only");
+  GM_CHECK_CUDA(cudaSetDevice(cfg->device));
+  gmvae_handle* h = new gmvae_handle();
+  h->cfg = *cfg;
+  const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
+  h->debug_flags = dbg ? atoi(dbg) : 0;
+  plan(h);
+  GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
+  DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull;
+  GM_CHECK_CUDA(cudaMemcpy(h->state, &s0, sizeof(s0), cudaMemcpyHostToDevice));
+  *out = h;
+  return 0;
+}
+
+void gmvae_destroy(gmvae_handle* h) {
+  if (!h) return;
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->comm) ncclCommDestroy(h->comm);
+  if (h->shadow_dev) cudaFree(h->shadow_dev);
+  if (h->state) cudaFree(h->state);
+  delete h;
+}
+
+int64_t gmvae_param_count(const gmvae_handle* h) { return h ? h->n_params : -1; }
+int64_t gmvae_grad_count(const gmvae_handle* h) { return h ? h->n_params + ACC_SLOTS : -1; }
+int gmvae_num_params(const gmvae_handle* h) { return h ? (int)h->table.size() : -1; }
+int gmvae_param_table(const gmvae_handle* h, gmvae_param_desc* out, int cap) {
+  GM_REQUIRE(h && out, "null argument");
+  int n = std::min(cap, (int)h->table.size());
+  for (int i = 0; i < n; ++i) out[i] = h->table[i];
+  return n;
+}
+size_t gmvae_workspace_bytes(const gmvae_handle* h) { return h ? h->ws_needed : 0; }
+int64_t gmvae_launch_count(const gmvae_handle* h) { return h ? h->launches : -1; }
+
+int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, float* adam_v, void* workspace, size_t workspace_bytes) {
+  GM_REQUIRE(h && params && grads && adam_m && adam_v && workspace, "null argument");
+  GM_REQUIRE(workspace_bytes >= h->ws_needed, "workspace too small");
+  GM_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(adam_m) && aligned16(adam_v), "buffers must be 16-byte aligned");
+  GM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
+  h->ws = reinterpret_cast<uint8_t*>(workspace); h->ws_bytes = workspace_bytes;
+  h->shadow_host.clear(); h->shadow_tiles = 0;
+  if (h->bf16_mode()) {
+    Mlp* mlps[4] = {&h->decoder, &h->encoder, &h->encoder_y, &h->prior_gmm};
+    for (Mlp* m : mlps)
+      for (auto& l : m->layers) {
+        l.w_bf16 = h->buf<bf16>("shadow.w." + std::to_string(l.w_off));
+        l.wt_bf16 = h->buf<bf16>("shadow.wt." + std::to_string(l.w_off));
+        ShadowEntry e;
+        e.w = params + l.w_off; e.w_bf16 = l.w_bf16; e.wt_bf16 = l.wt_bf16;
+        e.rows = l.in; e.cols = l.out; e.ld_w = l.ld_w; e.ld_wt = l.ld_wt;
+        e.tiles_x = (std::max(l.out, l.ld_w) + 31) / 32;
+        int tiles_y = (std::max(l.in, l.ld_wt) + 31) / 32;
+        e.tile_begin = h->shadow_tiles;
+        h->shadow_tiles += e.tiles_x * tiles_y;
+        h->shadow_host.push_back(e);
+      }
+    if (h->shadow_dev) cudaFree(h->shadow_dev);
+    GM_CHECK_CUDA(cudaMalloc(&h->shadow_dev, sizeof(ShadowEntry) * h->shadow_host.size()));
+    GM_CHECK_CUDA(cudaMemcpy(h->shadow_dev, h->shadow_host.data(), sizeof(ShadowEntry) * h->shadow_host.size(), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int gmvae_params_updated(gmvae_handle* h, void* stream) {
+  GM_TRY(check_ready(h));
+  return refresh_shadows(h, false, (cudaStream_t)stream);
+}
+
+int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
+                           const float* gumbel_u, void* stream) {
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(x_u8 != nullptr, "null input");
+  GM_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "batch must be in [1, max_batch]");
+  GM_REQUIRE(global_batch >= batch, "global_batch must be >= batch");
+  GM_REQUIRE(aligned16(x_u8), "x must be 16-byte aligned");
+  if (h->bf16_mode()) return forward_backward_impl<bf16>(h, x_u8, batch, global_batch, eps, gumbel_u, (cudaStream_t)stream);
+  return forward_backward_impl<float>(h, x_u8, batch, global_batch, eps, gumbel_u, (cudaStream_t)stream);
+}
+
+int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(loss_terms != nullptr, "null loss_terms");
+  finalize_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->grads + h->n_params, loss_terms);
+  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, (cudaStream_t)stream);
+  return 0;
+}
+
+int gmvae_adam_step(gmvae_handle* h, void* stream) {
+  GM_TRY(check_ready(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const gmvae_config& c = h->cfg;
+  int64_t n = h->n_params;
+  adam_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, n, c.learning_rate,
+                                                                  c.beta1, c.beta2, c.epsilon, h->state);
+  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  return refresh_shadows(h, true, st);
+}
+
+int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream) {
+  GM_REQUIRE(h && step, "null argument");
+  DeviceState s;
+  GM_CHECK_CUDA(cudaMemcpyAsync(&s, h->state, sizeof(s), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *step = s.step;
+  return 0;
+}
+int gmvae_set_step(gmvae_handle* h, int64_t step, void* stream) {
+  GM_REQUIRE(h, "null argument");
+  long long v = step;
+  GM_CHECK_CUDA(cudaMemcpyAsync(&h->state->step, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  GM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+int gmvae_set_seed(gmvae_handle* h, uint64_t seed) {
+  GM_REQUIRE(h, "null argument");
+  unsigned long long v = seed;
+  GM_CHECK_CUDA(cudaMemcpy(&h->state->seed, &v, sizeof(v), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gmvae_nccl_unique_id(char out[128]) {
+  GM_REQUIRE(out, "null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  ncclResult_t r = ncclGetUniqueId(&id);
+  if (r != ncclSuccess) { set_error(std::string("ncclGetUniqueId: ") + ncclGetErrorString(r)); return -5; }
+  memcpy(out, &id, 128);
+  return 0;
+}
+int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int rank) {
+  GM_REQUIRE(h && id, "null argument");
+  GM_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad world_size / rank");
+  ncclUniqueId uid; memcpy(&uid, id, 128);
+  GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+  ncclResult_t r = ncclCommInitRank(&h->comm, world_size, uid, rank);
+  if (r != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); return -5; }
+  h->world = world_size; h->rank = rank;
+  return 0;
+}
+int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
+  GM_TRY(check_ready(h));
+  if (!h->comm || h->world == 1) return 0;
+  ncclResult_t r = ncclAllReduce(h->grads, h->grads, (size_t)(h->n_params + ACC_SLOTS), ncclFloat, ncclSum, h->comm, (cudaStream_t)stream);
+  if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return -5; }
+  h->launches++;
+  return 0;
+}
+
+int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps, const float* gumbel_u,
+                     float* loss_terms, void* stream) {
+  GM_TRY(gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream));
+  GM_TRY(gmvae_allreduce_grads(h, stream));
+  if (loss_terms) GM_TRY(gmvae_finalize_loss(h, loss_terms, stream));
+  return gmvae_adam_step(h, stream);
+}
+
+int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
+                             const float* gumbel_u, float* loss_terms, void* stream) {
+  GM_TRY(check_ready(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  GM_REQUIRE(st != nullptr, "graph capture needs a non-default stream");
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  // Warm every kernel once outside capture (function attributes, tensor-map cache, lazy module load).
+  int saved = h->debug_flags; h->debug_flags &= ~DBG_SYNC_EACH;
+  GM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int r = gmvae_train_step(h, x_u8, batch, global_batch, eps, gumbel_u, loss_terms, stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  h->debug_flags = saved;
+  if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+  GM_CHECK_CUDA(e);
+  e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  GM_CHECK_CUDA(e);
+  return 0;
+}
+int gmvae_step_graph_launch(gmvae_handle* h, void* stream) {
+  GM_REQUIRE(h && h->graph_exec, "no captured graph");
+  GM_CHECK_CUDA(cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream));
+  return 0;
+}
+
+int gmvae_encode(gmvae_handle*, const uint8_t*, int, const float*, const float*, float*, float*, float*, void*) {
+  set_error("gmvae_encode: not built yet");
+  return -6;
+}
+int gmvae_decode(gmvae_handle*, const float*, int, float*, void*) {
+  set_error("gmvae_decode: not built yet");
+  return -6;
+}
+int gmvae_prior_table(gmvae_handle*, float*, float*, void*) {
+  set_error("gmvae_prior_table: not built yet");
+  return -6;
+}
+
+// ---- kernel-level test hook ------------------------------------------------------------------
+__global__ void dbg_to_bf16(const float* in, bf16* out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K, const float* A, const float* B,
+                     float* C, int split_k, void* stream) {
+  GM_REQUIRE(h && A && B && C, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GM_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * 4, st));
+  EpiAtomicAdd epi{C, (int64_t)N};
+  if (impl == 0) {
+    int64_t sAm = transA ? 1 : K, sAk = transA ? M : 1, sBk = transB ? 1 : N, sBn = transB ? K : 1;
+    GM_CHECK_CUDA((launch_gemm_simt<float, float, EpiAtomicAdd>(A, sAm, sAk, B, sBk, sBn, M, N, K, split_k, epi, st)));
+    return 0;
+  }
+  // tcgen05 path: operands converted to bf16 scratch (allocated here; test hook only).
+  // A stored [M,K] (transA=0 -> K-major) or [K,M] (transA=1 -> MN-major);
+  // B stored [K,N] (transB=0 -> MN-major) or [N,K] (transB=1 -> K-major).
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  GM_REQUIRE(a_mn == b_mn, "debug hook covers K-major x K-major and MN-major x MN-major");
+  bf16 *a16 = nullptr, *b16 = nullptr;
+  GM_CHECK_CUDA(cudaMalloc(&a16, (size_t)M * K * 2));
+  GM_CHECK_CUDA(cudaMalloc(&b16, (size_t)N * K * 2));
+  dbg_to_bf16<<<(unsigned)(((int64_t)M * K + 255) / 256), 256, 0, st>>>(A, a16, (int64_t)M * K);
+  dbg_to_bf16<<<(unsigned)(((int64_t)N * K + 255) / 256), 256, 0, st>>>(B, b16, (int64_t)N * K);
+  int r;
+  if (!a_mn) {
+    tc::Operand a{a16, K, M, K}, b{b16, K, N, K};
+    r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, epi, st);
+  } else {
+    tc::Operand a{a16, M, M, K}, b{b16, N, N, K};
+    r = N <= 64 ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
+                : tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(a16); cudaFree(b16);
+  if (r != 0) return r;
+  GM_CHECK_CUDA(e);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// gemm_tc.cuh -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (sm_100a), hand-written:
+// TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (one issuing
+// thread, accumulator in TMEM) -> tcgen05.ld -> fused epilogue functor (epilogue.cuh).
+//
+//   C[M,N] (+)= A1[M,K1] * B1[K1,N] + A2[M,K2] * B2[K2,N]        (second segment optional)
+//
+// The second K segment accumulates into the same TMEM tile; it removes the reference's
+// tf.concat([x, y]) (base.py:66): [x,y] @ W = x @ W[:D] + y @ W[D:].
+// Operand "majorness" is a template parameter: K-major operands come from row-major
+// [rows, K] tensors (activations in forward/dgrad, transposed weight copies); MN-major
+// operands come from row-major [K, rows] tensors and are what the weight-gradient
+// contraction dW = X^T dY needs (both X and dY are stored [batch, features], the reduction
+// runs over the batch), so no transposed activation copies are ever written.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gmvae {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must end as a trapped launch (an error the host sees), never as
+// a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMA -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ---- tcgen05 -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint64_t adesc, uint64_t bdesc, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors ---------------------------------------------------------------------------
+// Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"; same bit layout as
+// cute::UMMA::SmemDescriptor): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48)
+// version=1, [61,64) layout (2 = 128-byte swizzle).
+//   K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major, 128B swizzle: slabs of 64 MN-elements x BLOCK_K k-rows; k-rows 128 B apart,
+//   8-k-row groups 1024 B apart (SBO), slabs BLOCK_K*128 B apart (LBO).
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  const uint64_t lbo = MN_MAJOR ? (uint64_t)(BLOCK_K * 128) : 0;
+  const uint64_t sbo = 1024;
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// bytes to add to the start address per UMMA_K (=16 elements of K)
+template <bool MN_MAJOR>
+__device__ __forceinline__ constexpr uint32_t desc_k_step() { return MN_MAJOR ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4; }
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16
+// [10,13), a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+template <int N, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+template <int BLOCK_N> __host__ __device__ constexpr int stages_for() { return BLOCK_N >= 256 ? 4 : 3; }
+template <int BLOCK_N> __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2; }
+template <int BLOCK_N> __host__ __device__ constexpr int smem_bytes() { return stages_for<BLOCK_N>() * stage_bytes<BLOCK_N>() + 1024 /*align*/ + 256 /*barriers*/; }
+
+struct GemmMaps {
+  CUtensorMap a1, b1, a2, b2;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS)
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int kb2, int kb_per_split, Epi epi_in) {
+  constexpr int STAGES = stages_for<BLOCK_N>();
+  constexpr int STAGE_BYTES = stage_bytes<BLOCK_N>();
+  constexpr int TMEM_COLS = tmem_cols_for(BLOCK_N);
+  constexpr int CW = (BLOCK_N % 32 == 0) ? 32 : 16;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
+  static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B is loaded in 64-column slabs");
+  static_assert((BLOCK_N * BLOCK_K * 2) % 1024 == 0, "stage buffers must stay 1024-byte aligned");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const int kb_total = kb1 + kb2;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(kb_total, kb_begin + kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  if (nkb <= 0) return;  // uniform across the CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool seg2 = kb >= kb1;
+        const CUtensorMap* ta = seg2 ? &maps.a2 : &maps.a1;
+        const CUtensorMap* tb = seg2 ? &maps.b2 : &maps.b1;
+        const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        if (A_MN) {
+#pragma unroll
+          for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+        } else {
+          tma_load_2d(ta, &full_bar[stage], sa, k_elem, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(tb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
+        } else {
+          tma_load_2d(tb, &full_bar[stage], sb, k_elem, n0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<A_MN>(sa);
+        const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          umma_bf16(adesc + (uint64_t)(k * desc_k_step<A_MN>()), bdesc + (uint64_t)(k * desc_k_step<B_MN>()), tmem_base, idesc,
+                    (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====
+    Epi epi = epi_in;
+    const int quad = warp & 3;
+    const int m = m0 + quad * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += CW) {
+      float v[CW];
+      if constexpr (CW == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
+      const int n = n0 + c;
+      if (m < M && n < N) epi.template row<CW>(m, n, v, min(CW, N - n));
+    }
+    epi.finish_warp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+// 2-D bf16 tensor, row-major [outer, inner] with `outer_stride` elements between rows;
+// box = {box_inner (<= 64), box_outer}, 128-byte swizzle, out-of-bounds elements read as zero.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
+                   uint32_t box_inner, uint32_t box_outer);
+
+// Operand description given to launch_gemm_tc: a row-major bf16 matrix.
+//   K-major operand  : stored [rows(M or N), K],  ld = row stride
+//   MN-major operand : stored [K, rows(M or N)],  ld = row stride
+struct Operand {
+  const bf16* ptr; int64_t ld; int rows; int k;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
+int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, const Operand* B2, int M, int N, int split_k,
+                   const Epi& epi, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, Epi>;
+  if (!attr_set) {
+    GM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BLOCK_N>()));
+    attr_set = true;
+  }
+  GemmMaps maps;
+  auto mk = [&](CUtensorMap* m, const Operand& o, bool mn, int box_rows) -> int {
+    if (mn) return make_tmap_bf16(m, o.ptr, (uint64_t)o.rows, (uint64_t)o.k, (uint64_t)o.ld, 64, BLOCK_K);
+    return make_tmap_bf16(m, o.ptr, (uint64_t)o.k, (uint64_t)o.rows, (uint64_t)o.ld, BLOCK_K, (uint32_t)box_rows);
+  };
+  GM_TRY(mk(&maps.a1, A1, A_MN, BLOCK_M));
+  GM_TRY(mk(&maps.b1, B1, B_MN, BLOCK_N));
+  int kb1 = (A1.k + BLOCK_K - 1) / BLOCK_K, kb2 = 0;
+  if (A2 && B2) {
+    GM_TRY(mk(&maps.a2, *A2, A_MN, BLOCK_M));
+    GM_TRY(mk(&maps.b2, *B2, B_MN, BLOCK_N));
+    kb2 = (A2->k + BLOCK_K - 1) / BLOCK_K;
+  } else {
+    maps.a2 = maps.a1; maps.b2 = maps.b1;
+  }
+  int kb_total = kb1 + kb2;
+  if (split_k < 1) split_k = 1;
+  int per = (kb_total + split_k - 1) / split_k;
+  split_k = (kb_total + per - 1) / per;
+  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M, split_k);
+  kern<<<grid, NUM_THREADS, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, epi);
+  GM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace gmvae

@@ -1,0 +1,390 @@
+// kernels.cuh -- the non-GEMM kernels of the training step: input conversion, noise, the
+// distribution "heads" (Gumbel-softmax / entropy, reparameterised Gaussian sample and KL terms,
+// mixture prior), bias gradients, TF-form Adam and the bf16 operand refresh.
+#pragma once
+#include "common.cuh"
+
+namespace gmvae {
+
+// Loss accumulators live in the tail of the gradient buffer (so one all-reduce covers them).
+enum { ACC_NLL = 0, ACC_KL = 1, ACC_NENT = 2, ACC_SLOTS = 8 };
+
+struct DeviceState {           // owned by the handle, lives on the device
+  long long step;              // global_step (runners.py:171)
+  unsigned long long seed;
+};
+
+// ---- x: bool bytes -> GEMM operand type (vae.py:75, gmvae.py:86,104: tf.cast(x, float32)) ----
+template <typename T>
+__global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    uint4 t = *reinterpret_cast<const uint4*>(x + i);
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[i + j] = from_f32<T>((float)p[j]);
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = from_f32<T>((float)x[j]);
+  }
+}
+
+// ---- noise (only when the caller does not inject it) -----------------------------------------
+// eps ~ N(0,1) (tf.random_normal inside MultivariateNormalDiag.sample), u ~ U(tiny,1)
+// (RelaxedOneHotCategorical.sample).  Keyed by (seed, step, stream id, element index).
+__global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
+                                  const DeviceState* st, uint64_t rank_stream) {
+  const uint64_t seed = st->seed, step = (uint64_t)st->step;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t q_eps = (n_eps + 3) / 4, q_u = (n_u + 3) / 4;
+  uint32_t r[4];
+  if (i < q_eps) {
+    Philox::gen(seed ^ (step * 0x9E3779B97F4A7C15ull), rank_stream * 2, (uint64_t)i, r);
+    float a0 = sqrtf(-2.f * logf(u01(r[0]))), a1 = sqrtf(-2.f * logf(u01(r[2])));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u01(r[1]), &s0, &c0);
+    sincospif(2.f * u01(r[3]), &s1, &c1);
+    float v[4] = {a0 * c0, a0 * s0, a1 * c1, a1 * s1};
+    for (int j = 0; j < 4; ++j)
+      if (i * 4 + j < n_eps) eps[i * 4 + j] = v[j];
+  } else if (i < q_eps + q_u) {
+    int64_t k = i - q_eps;
+    Philox::gen(seed ^ (step * 0x9E3779B97F4A7C15ull), rank_stream * 2 + 1, (uint64_t)k, r);
+    for (int j = 0; j < 4; ++j)
+      if (k * 4 + j < n_u) u[k * 4 + j] = u01(r[j]);
+  }
+}
+
+// ---- q(y|x) head, forward (gmvae.py:238-240, 262-263; utils.py:165-170) ------------------------
+// One warp per row.  p = softmax(l); nent += sum_k p log p / B;  y = softmax((l + g)/T),
+// g = -log(-log u).  y is written twice: fp32 for the backward pass and as the zero-padded GEMM
+// operand of encoder_gmm layer 0 / prior_gmm.
+constexpr int HEAD_MAXK = 128;
+template <typename ActT>
+__global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ u, int B, int K, float inv_T,
+                                  float inv_bg, float* __restrict__ y_f32, ActT* __restrict__ y_act, int ld_yact,
+                                  float* __restrict__ acc) {
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float ent = 0.f;
+  if (row < B) {
+    float l[HEAD_MAXK / 32], a[HEAD_MAXK / 32];
+    float ml = -INFINITY, ma = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      l[i] = -INFINITY; a[i] = -INFINITY;
+      if (k < K) {
+        l[i] = logits[(int64_t)row * K + k];
+        float uu = u[(int64_t)row * K + k];
+        a[i] = (l[i] - logf(-logf(uu))) * inv_T;
+      }
+      ml = fmaxf(ml, l[i]); ma = fmaxf(ma, a[i]);
+    }
+    ml = warp_max(ml); ma = warp_max(ma);
+    float sl = 0.f, sa = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) { sl += expf(l[i] - ml); sa += expf(a[i] - ma); }
+    }
+    sl = warp_sum(sl); sa = warp_sum(sa);
+    const float lse = ml + logf(sl), inv_sa = 1.f / sa;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) {
+        float logp = l[i] - lse;
+        ent += expf(logp) * logp;
+        float y = expf(a[i] - ma) * inv_sa;
+        y_f32[(int64_t)row * K + k] = y;
+        y_act[(int64_t)row * ld_yact + k] = from_f32<ActT>(y);
+      } else if (k < ld_yact) {
+        y_act[(int64_t)row * ld_yact + k] = from_f32<ActT>(0.f);
+      }
+    }
+  }
+  float s = block_sum(ent, scratch);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_NENT, s * inv_bg);
+}
+
+// ---- q(y|x) head, backward --------------------------------------------------------------------
+// dl = softmax-Jacobian((l+g)/T)^T dy / T  +  d nent/dl,   d nent/dl_j = p_j (log p_j - sum p log p)/B
+template <int DUMMY = 0>
+__global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y_f32,
+                                  const float* __restrict__ dy, int B, int K, float inv_T, float inv_bg,
+                                  float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float l[HEAD_MAXK / 32], y[HEAD_MAXK / 32], g[HEAD_MAXK / 32];
+  float ml = -INFINITY, ydy = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+    int k = lane + 32 * i;
+    l[i] = -INFINITY; y[i] = 0.f; g[i] = 0.f;
+    if (k < K) {
+      l[i] = logits[(int64_t)row * K + k];
+      y[i] = y_f32[(int64_t)row * K + k];
+      g[i] = dy ? dy[(int64_t)row * K + k] : 0.f;
+    }
+    ml = fmaxf(ml, l[i]);
+    ydy += y[i] * g[i];
+  }
+  ml = warp_max(ml); ydy = warp_sum(ydy);
+  float sl = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i)
+    if (lane + 32 * i < K) sl += expf(l[i] - ml);
+  sl = warp_sum(sl);
+  const float lse = ml + logf(sl);
+  float plogp = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i)
+    if (lane + 32 * i < K) { float lp = l[i] - lse; plogp += expf(lp) * lp; }
+  plogp = warp_sum(plogp);
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+    int k = lane + 32 * i;
+    if (k < K) {
+      float lp = l[i] - lse;
+      dlogits[(int64_t)row * K + k] = y[i] * (g[i] - ydy) * inv_T + expf(lp) * (lp - plogp) * inv_bg;
+    }
+  }
+}
+
+// ---- q(z|.) head, forward (base.py:69-70; gmvae.py:248,258; vae.py:171,181) ---------------------
+// enc_out = [mu | raw] (B x 2Z).  sigma = max(softplus(raw + c), sigma_min); z = mu + sigma eps.
+// KL accumulator gets log q(z) - log p(z) summed over the batch, divided by the global batch:
+//   log q(z) = -0.5 eps^2 - log sigma (-Z/2 log 2pi, cancels against the prior's constant)
+//   prior_mode 0 (VAE):       log p = -0.5 z^2
+//   prior_mode 1 (VAE_GMP):   handled by gmp_prior_kernel; only the log q part is added here
+//   prior_mode 2 (GMVAE, R):  prior_out = [mu_p | raw_p] per row, log p = -0.5 ((z-mu_p)/s_p)^2 - log s_p
+template <typename ActT>
+__global__ void head_z_fwd_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
+                                  const float* __restrict__ prior_out, int prior_mode, int B, int Z, float c,
+                                  float sigma_min, float inv_bg, ActT* __restrict__ z_act, float* __restrict__ z_f32,
+                                  float* __restrict__ acc) {
+  __shared__ float scratch[32];
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float kl = 0.f;
+  if (i < (int64_t)B * Z) {
+    int b = (int)(i / Z), j = (int)(i % Z);
+    float mu = enc_out[(int64_t)b * 2 * Z + j], raw = enc_out[(int64_t)b * 2 * Z + Z + j];
+    float sg = fmaxf(softplus_f(raw + c), sigma_min);
+    float e = eps[i];
+    float z = fmaf(sg, e, mu);
+    z_act[i] = from_f32<ActT>(z);
+    if (z_f32) z_f32[i] = z;
+    float logq = -0.5f * e * e - logf(sg);
+    float logp = 0.f;
+    if (prior_mode == 0) {
+      logp = -0.5f * z * z;
+    } else if (prior_mode == 2) {
+      float mp = prior_out[(int64_t)b * 2 * Z + j], rp = prior_out[(int64_t)b * 2 * Z + Z + j];
+      float sp = fmaxf(softplus_f(rp + c), sigma_min);
+      float t = (z - mp) / sp;
+      logp = -0.5f * t * t - logf(sp);
+    }
+    kl = logq - logp;
+  }
+  float s = block_sum(kl, scratch);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+}
+
+// ---- q(z|.) head, backward ---------------------------------------------------------------------
+// dz = dz_dec + d kl/dz;  d mu_q = dz;  d sigma_q = dz eps - 1/(B sigma_q);  d raw = d sigma * sigmoid(raw+c)
+// GMVAE: d mu_p = -(z-mu_p)/(B s_p^2); d s_p = (1/s_p - (z-mu_p)^2/s_p^3)/B.
+template <typename ActT>
+__global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
+                                  const float* __restrict__ prior_out, const float* __restrict__ dz_dec,
+                                  const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c,
+                                  float sigma_min, float inv_bg, ActT* __restrict__ d_enc_out,
+                                  float* __restrict__ d_prior_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Z) return;
+  int b = (int)(i / Z), j = (int)(i % Z);
+  float mu = enc_out[(int64_t)b * 2 * Z + j], raw = enc_out[(int64_t)b * 2 * Z + Z + j];
+  float spq = softplus_f(raw + c);
+  float sg = fmaxf(spq, sigma_min);
+  float e = eps[i];
+  float z = fmaf(sg, e, mu);
+  float dz = dz_dec[i];
+  if (prior_mode == 0) {
+    dz += z * inv_bg;
+  } else if (prior_mode == 1) {
+    dz += dz_prior[i];
+  } else {
+    float mp = prior_out[(int64_t)b * 2 * Z + j], rp = prior_out[(int64_t)b * 2 * Z + Z + j];
+    float spp = softplus_f(rp + c);
+    float sp = fmaxf(spp, sigma_min);
+    float d = z - mp;
+    float isp2 = 1.f / (sp * sp);
+    dz += d * isp2 * inv_bg;
+    float dsp = (1.f / sp - d * d * isp2 / sp) * inv_bg;
+    d_prior_out[(int64_t)b * 2 * Z + j] = -d * isp2 * inv_bg;
+    d_prior_out[(int64_t)b * 2 * Z + Z + j] = spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f;
+  }
+  float dsg = dz * e - inv_bg / sg;
+  d_enc_out[(int64_t)b * 2 * Z + j] = from_f32<ActT>(dz);
+  d_enc_out[(int64_t)b * 2 * Z + Z + j] = from_f32<ActT>(spq >= sigma_min ? dsg * sigmoid_f(raw + c) : 0.f);
+}
+
+// ---- VAE_GMP mixture prior (vae.py:231-244, 181): forward value and every gradient -------------
+// log p(z) = logsumexp_k [ log_softmax(m)_k + log N(z; loc_k, softplus(raw_scale_k)) ]
+// One warp per row; lanes stride over Z.  Adds -log p / B to the KL accumulator, writes
+// d kl/dz (prior part) to dz_prior, and accumulates d loc, d raw_scale_diag, d mixture_logits.
+__global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __restrict__ loc,
+                                 const float* __restrict__ raw_scale, const float* __restrict__ mix_logits, int B, int K,
+                                 int Z, float inv_bg, float* __restrict__ dz_prior, float* __restrict__ d_loc,
+                                 float* __restrict__ d_raw_scale, float* __restrict__ d_mix, float* __restrict__ acc) {
+  extern __shared__ float sm[];  // per warp: K log-weights
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* lw = sm + w * K;
+  const int row = blockIdx.x * nw + w;
+  float neg_logp = 0.f;
+  if (row < B) {
+    // log_softmax of the mixture logits
+    float mm = -INFINITY;
+    for (int k = lane; k < K; k += 32) mm = fmaxf(mm, mix_logits[k]);
+    mm = warp_max(mm);
+    float ms = 0.f;
+    for (int k = lane; k < K; k += 32) ms += expf(mix_logits[k] - mm);
+    ms = warp_sum(ms);
+    const float mlse = mm + logf(ms);
+    float best = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int j = lane; j < Z; j += 32) {
+        float sc = softplus_f(raw_scale[k * Z + j]);
+        float t = (z[(int64_t)row * Z + j] - loc[k * Z + j]) / sc;
+        s += -0.5f * t * t - logf(sc);
+      }
+      s = warp_sum(s) + (mix_logits[k] - mlse);
+      if (lane == 0) lw[k] = s;
+      best = fmaxf(best, s);
+    }
+    __syncwarp();
+    float se = 0.f;
+    for (int k = lane; k < K; k += 32) se += expf(lw[k] - best);
+    se = warp_sum(se);
+    const float logp = best + logf(se);
+    neg_logp = lane == 0 ? -logp : 0.f;
+    for (int j = lane; j < Z; j += 32) dz_prior[(int64_t)row * Z + j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float r = expf(lw[k] - logp);  // responsibility
+      if (lane == 0) atomicAdd(d_mix + k, -(r - expf(mix_logits[k] - mlse)) * inv_bg);
+      for (int j = lane; j < Z; j += 32) {
+        float raw = raw_scale[k * Z + j];
+        float sc = softplus_f(raw);
+        float d = z[(int64_t)row * Z + j] - loc[k * Z + j];
+        float is2 = 1.f / (sc * sc);
+        dz_prior[(int64_t)row * Z + j] += r * d * is2 * inv_bg;
+        atomicAdd(d_loc + k * Z + j, -r * d * is2 * inv_bg);
+        float dsc = -r * (d * d * is2 / sc - 1.f / sc) * inv_bg;
+        atomicAdd(d_raw_scale + k * Z + j, dsc * sigmoid_f(raw));
+      }
+    }
+  }
+  float s = block_sum(neg_logp, scratch);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+}
+
+// ---- bias gradients: db[n] += sum_m dY[m,n] -----------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, int M, int N, int rows_per_block, float* __restrict__ db) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int r = r0 + ty; r < r1; r += 8) s += to_f32<T>(dY[(int64_t)r * ld + n]);
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += sm[i][tx];
+    if (n < N) atomicAdd(db + n, s);
+  }
+}
+
+// ---- loss terms ---------------------------------------------------------------------------------
+__global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    float nll = acc[ACC_NLL], kl = acc[ACC_KL], ne = acc[ACC_NENT];
+    out[0] = nll + kl + ne;  // gmvae.py:267 / vae.py:185
+    out[1] = nll; out[2] = kl; out[3] = ne;
+  }
+}
+
+// ---- tf.train.AdamOptimizer (runners.py:181-183) ------------------------
+// lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// theta -= lr_t m / (sqrt(v) + eps).   t = step+1 read from the device; one flat pass.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float lr, float b1, float b2, float eps, const DeviceState* st) {
+  __shared__ float lr_t_s;
+  if (threadIdx.x == 0) {
+    double t = (double)(st->step + 1);
+    lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
+  __syncthreads();
+  const float lr_t = lr_t_s;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+    float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float* P = &pp.x; const float* G = &gg.x; float* Mm = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      Mm[j] = b1 * Mm[j] + (1.f - b1) * G[j];
+      V[j] = b2 * V[j] + (1.f - b2) * G[j] * G[j];
+      P[j] -= lr_t * Mm[j] / (sqrtf(V[j]) + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+  } else {
+    for (int64_t k = i; k < n; ++k) {
+      float mk = b1 * m[k] + (1.f - b1) * g[k];
+      float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
+      m[k] = mk; v[k] = vk;
+      p[k] -= lr_t * mk / (sqrtf(vk) + eps);
+    }
+  }
+}
+
+// ---- bf16 operand copies of the weight matrices --------------------------------------------------
+// For W [rows=in, cols=out] fp32: w_bf16 [in, ld_w] (dgrad B operand, K-major over `out`) and
+// wt_bf16 [out, ld_wt] (forward B operand, K-major over `in`).  One entry per matrix; a 32x32
+// tile per block, transposed through shared memory.  Block (0,0,0) also advances global_step.
+struct ShadowEntry {
+  const float* w; bf16* w_bf16; bf16* wt_bf16;
+  int rows, cols, ld_w, ld_wt;
+  int tiles_x, tile_begin;   // tiles along cols; first flat tile index of this entry
+};
+__global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, int n_entries, DeviceState* st, int bump_step) {
+  __shared__ float tile[32][33];
+  if (bump_step && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) st->step += 1;
+  int e = 0;
+  while (e + 1 < n_entries && (int)blockIdx.x >= entries[e + 1].tile_begin) ++e;
+  const ShadowEntry E = entries[e];
+  const int t = blockIdx.x - E.tile_begin;
+  const int c0 = (t % E.tiles_x) * 32, r0 = (t / E.tiles_x) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    float v = (r < E.rows && c < E.cols) ? E.w[(int64_t)r * E.cols + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (E.w_bf16 && r < E.rows && c < E.ld_w) E.w_bf16[(int64_t)r * E.ld_w + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (E.wt_bf16) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int c = c0 + i, r = r0 + threadIdx.x;  // output row = c (an `out` index), output col = r (an `in` index)
+      if (c < E.cols && r < E.ld_wt) E.wt_bf16[(int64_t)c * E.ld_wt + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+__global__ void bump_step_kernel(DeviceState* st) { st->step += 1; }
+
+}  // namespace gmvae

@@ -1,0 +1,56 @@
+"""VAE / VAE with a Gaussian-mixture prior -- mirror of /root/reference/scripts/vae.py."""
+from __future__ import annotations
+
+from typing import Optional
+
+from . import base
+from ._model import _EngineBacked
+
+
+class VAE(_EngineBacked):
+    """vae.py:11-123.  `prior` is None for the standard normal (vae.py:247-250) or the string
+    'mixture' for the learned MixtureSameFamily prior (vae.py:231-244)."""
+    _model_kind = "vae"
+
+    def __init__(self, prior, decoder, encoder, mix_components, random_seed):
+        self._prior = prior
+        self._decoder = decoder
+        self._encoder = encoder
+        self.mix_components = mix_components
+        self.random_seed = random_seed
+        self._init_backing()
+
+    def _engine_kwargs(self):
+        enc, dec = self._encoder, self._decoder
+        return dict(model="vae_gmp" if self.mix_components > 1 else "vae", data_size=dec.size, latent_size=enc.size,
+                    hidden_sizes=enc.hidden_layer_sizes or [], mixture_components=self.mix_components,
+                    sigma_min=enc._sigma_min, raw_sigma_bias=enc._raw_sigma_bias, gen_bias_init=dec._bias_init)
+
+    def prior(self):
+        return self._prior
+
+
+class TrainableVAE(VAE):
+    """vae.py:126-188."""
+
+    def __init__(self, prior, decoder, encoder, mix_components=1, random_seed=None):
+        super().__init__(prior, decoder, encoder, mix_components, random_seed)
+
+    def run_model(self, images, targets, eps=None):
+        """loss = nll + kl_div_z (vae.py:153-188); gradients of every variable are computed in the
+        same pass (runners.py:182).  `eps` optionally injects the N(0,1) noise of q_z.sample()."""
+        return self._run(images, targets, eps, None)
+
+
+def create_vae(data_size, latent_size, mixture_components=1, fcnet_hidden_sizes=None, hidden_activation_fn="relu",
+               sigma_min=0.001, raw_sigma_bias=0.25, gen_bias_init=0.0, random_seed=None) -> TrainableVAE:
+    """Factory with the reference's signature and defaults (vae.py:191-271)."""
+    if fcnet_hidden_sizes is None:
+        fcnet_hidden_sizes = [latent_size]                      # vae.py:228-229
+    prior = "mixture" if mixture_components > 1 else None
+    decoder = base.ConditionalBernoulli(size=data_size, hidden_layer_sizes=fcnet_hidden_sizes,
+                                        hidden_activation_fn=hidden_activation_fn, bias_init=gen_bias_init, name="decoder")
+    encoder = base.ConditionalNormal(size=latent_size, hidden_layer_sizes=fcnet_hidden_sizes,
+                                     hidden_activation_fn=hidden_activation_fn, sigma_min=sigma_min,
+                                     raw_sigma_bias=raw_sigma_bias, name="encoder")
+    return TrainableVAE(prior, decoder, encoder, mix_components=mixture_components, random_seed=random_seed)

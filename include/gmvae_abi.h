@@ -1,0 +1,167 @@
+/*
+ * gmvae_abi.h -- C ABI of libgmvae_b200.so, the B200-native (sm_100a) training step of
+ * mazrk7/gmvae (VAE / VAE_GMP / GMVAE on flattened binarised images).
+ *
+ * The reference has no FFI of its own: its hot path sits behind a Python object API
+ * (scripts/{base,vae,gmvae}.py) that builds a TF-1.13 graph, and behind
+ * `sess.run([train_op, global_step])` (scripts/runners.py:231-232).  This header is the
+ * boundary a maintainer binds instead of that graph; each entry point names the reference
+ * lines it replaces.  The Python host in gmvae_b200/ binds it with ctypes; INTEGRATION.md
+ * shows the stub.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++ / torch types.
+ *   - every buffer is a DEVICE pointer owned by the caller (PyTorch tensors in our host);
+ *     the library owns only the handle, its TMA descriptors, CUDA graph and NCCL communicator.
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as
+ *     void*); no hidden synchronisation, no allocation after gmvae_bind().
+ *   - int return: 0 = OK, negative = error; message via gmvae_last_error() (thread-local).
+ *   - a handle is bound to one device and is not thread-safe; one process per GPU.
+ *   - there is NO CPU fallback: every entry point that computes requires an sm_100 device.
+ */
+#ifndef GMVAE_ABI_H_
+#define GMVAE_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GMVAE_API __attribute__((visibility("default")))
+#else
+#define GMVAE_API
+#endif
+
+#define GMVAE_ABI_VERSION 1
+#define GMVAE_MAX_HIDDEN_LAYERS 8
+#define GMVAE_NAME_LEN 64
+
+/* run_gmvae.py:14-16 `--model` */
+enum { GMVAE_MODEL_VAE = 0, GMVAE_MODEL_VAE_GMP = 1, GMVAE_MODEL_GMVAE = 2 };
+/* objective: REFERENCE = what gmvae.py:238-267 computes (one relaxed y, one z, MC KL);
+ *            MARGINAL  = q(y|x)-weighted per-component ELBO with analytic KL (north_star). */
+enum { GMVAE_OBJECTIVE_REFERENCE = 0, GMVAE_OBJECTIVE_MARGINAL = 1 };
+/* precision of the GEMM path: FP32 = SIMT validation mode (rel 1e-5), BF16 = tcgen05 tiles */
+enum { GMVAE_PRECISION_FP32 = 0, GMVAE_PRECISION_BF16 = 1 };
+
+typedef struct gmvae_handle gmvae_handle;
+
+/* What runners.create_model (runners.py:65-103) passes to create_gmvae / create_vae
+ * (gmvae.py:277-287, vae.py:191-200) plus the optimiser of runners.py:181. */
+typedef struct gmvae_config {
+  int32_t abi_version;        /* GMVAE_ABI_VERSION */
+  int32_t model;              /* GMVAE_MODEL_* */
+  int32_t objective;          /* GMVAE_OBJECTIVE_* (GMVAE only) */
+  int32_t precision;          /* GMVAE_PRECISION_* */
+  int32_t data_size;          /* 784 */
+  int32_t latent_size;        /* --latent_size */
+  int32_t mixture_components; /* --mixture_components */
+  int32_t num_hidden;         /* len(fcnet_hidden_sizes) */
+  int32_t hidden_sizes[GMVAE_MAX_HIDDEN_LAYERS];
+  int32_t max_batch;          /* largest per-device batch this handle will see */
+  float sigma_min;            /* runners.py:84 (0.0) */
+  float raw_sigma_bias;       /* runners.py:85 (0.5) */
+  float gen_bias_init;        /* gmvae.py:284 */
+  float temperature;          /* runners.py:86 (1.0) */
+  float learning_rate;        /* --learning_rate; tf.train.AdamOptimizer defaults below */
+  float beta1, beta2, epsilon;
+  int32_t device;             /* CUDA ordinal */
+  int32_t reserved[7];
+} gmvae_config;
+
+/* One trainable variable of the flat parameter buffer.  Names are the reference's TF
+ * variable names (`{module}_fcnet/linear_{i}/{w,b}`, `loc`, `raw_scale_diag`,
+ * `mixture_logits`; base.py:53,60 / vae.py:233-238) so a TF checkpoint maps 1:1. */
+typedef struct gmvae_param_desc {
+  char name[GMVAE_NAME_LEN];
+  int64_t offset;             /* in floats, into params / grads / adam_m / adam_v */
+  int32_t rows, cols;         /* weights [rows=in, cols=out] row-major; vectors rows=1 */
+} gmvae_param_desc;
+
+/* Construction = create_gmvae / create_vae (gmvae.py:277-355, vae.py:191-271). */
+GMVAE_API int gmvae_create(const gmvae_config* cfg, gmvae_handle** out);
+GMVAE_API void gmvae_destroy(gmvae_handle* h);
+
+/* Flat layout of tf.trainable_variables() (runners.py:182). param_count includes the
+ * 16-byte alignment padding between tensors; grad_count = param_count + 8 (the tail holds
+ * the un-normalised loss accumulators so that one all-reduce covers both). */
+GMVAE_API int64_t gmvae_param_count(const gmvae_handle* h);
+GMVAE_API int64_t gmvae_grad_count(const gmvae_handle* h);
+GMVAE_API int gmvae_num_params(const gmvae_handle* h);
+GMVAE_API int gmvae_param_table(const gmvae_handle* h, gmvae_param_desc* out, int cap);
+
+GMVAE_API size_t gmvae_workspace_bytes(const gmvae_handle* h);
+/* params/adam_m/adam_v: float[param_count]; grads: float[grad_count]; workspace: bytes above. */
+GMVAE_API int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, float* adam_v,
+               void* workspace, size_t workspace_bytes);
+/* Call after writing `params` from outside (initialisation, checkpoint restore): refreshes
+ * the bf16 operand copies the tensor-core path reads. */
+GMVAE_API int gmvae_params_updated(gmvae_handle* h, void* stream);
+
+/* loss = model.run_model(images, targets[, labels]) (gmvae.py:223-274, vae.py:153-188)
+ * followed by opt.compute_gradients (runners.py:182).
+ *   x_u8        [batch, data_size] bytes in {0,1} (the reference feeds bool; targets == images)
+ *   global_batch divisor of the batch means (== batch on one GPU; sum over ranks under DP)
+ *   eps         [batch, Z] (REFERENCE / VAE) or [batch, K, Z] (MARGINAL) N(0,1) noise, or NULL
+ *               to draw it on the device (Philox, keyed by seed and the device step counter)
+ *   gumbel_u    [batch, K] uniforms in [tiny,1) for the relaxed one-hot sample, or NULL
+ *   loss_terms  device float[4] = {loss, nll, kl_div_z, nent}; written by
+ *               gmvae_finalize_loss (after the all-reduce under DP)
+ * Gradients land in `grads` (overwritten). */
+GMVAE_API int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch,
+                           const float* eps, const float* gumbel_u, void* stream);
+GMVAE_API int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream);
+
+/* opt.apply_gradients (runners.py:183): TF-form Adam on the flat buffer, then
+ * global_step += 1 and the beta-power accumulators advance (all on the device). */
+GMVAE_API int gmvae_adam_step(gmvae_handle* h, void* stream);
+GMVAE_API int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream);   /* synchronises */
+GMVAE_API int gmvae_set_step(gmvae_handle* h, int64_t step, void* stream);    /* checkpoint restore */
+GMVAE_API int gmvae_set_seed(gmvae_handle* h, uint64_t seed);
+
+/* Data parallelism (new; the reference is single-device, runners.py:193): one NCCL
+ * all-reduce(sum) over grads[0:grad_count].  No-op when no communicator is attached. */
+GMVAE_API int gmvae_nccl_unique_id(char out[128]);
+GMVAE_API int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int rank);
+GMVAE_API int gmvae_allreduce_grads(gmvae_handle* h, void* stream);
+
+/* One whole iteration of the hot loop `sess.run([train_op, global_step])`
+ * (runners.py:231-232): forward_backward -> allreduce -> finalize_loss -> adam_step.
+ * capture() records it once into a CUDA graph for fixed pointers; launch() replays it. */
+GMVAE_API int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch,
+                     const float* eps, const float* gumbel_u, float* loss_terms, void* stream);
+GMVAE_API int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch,
+                             const float* eps, const float* gumbel_u, float* loss_terms,
+                             void* stream);
+GMVAE_API int gmvae_step_graph_launch(gmvae_handle* h, void* stream);
+
+/* Forward-only helpers behind the model classes' inference methods
+ * (gmvae.py:109-188, vae.py:80-123).  out buffers are device float arrays.
+ *   encode : x -> (optional) logits_y [batch,K], z_mean [batch,Z], z_sample [batch,Z]
+ *   decode : z [n,Z] -> Bernoulli mean sigmoid(logits) [n, data_size]
+ *   prior  : GMVAE prior_gmm(one_hot(k)) table -> mu [K,Z], sigma [K,Z] */
+GMVAE_API int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, const float* eps,
+                 const float* gumbel_u, float* logits_y, float* z_mean, float* z_sample,
+                 void* stream);
+GMVAE_API int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* stream);
+GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream);
+
+/* Kernel-level test hook: C[M,N] = A[M,K] * B[K,N] through the same GEMM kernels the step
+ * uses (impl 0 = fp32 SIMT, 1 = tcgen05 bf16).  A, B, C are device float arrays, row-major;
+ * transA/transB say the stored matrix is the transpose ([K,M] / [N,K]).  Used by tests/. */
+GMVAE_API int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K,
+                     const float* A, const float* B, float* C, int split_k, void* stream);
+
+/* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches"). */
+GMVAE_API int64_t gmvae_launch_count(const gmvae_handle* h);
+
+GMVAE_API const char* gmvae_last_error(void);
+GMVAE_API const char* gmvae_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMVAE_ABI_H_ */
