@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- GMVAE training-step throughput (fwd + bwd + Adam) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's step restated on the host CPU
+
+One "step" = one iteration of the reference's hot loop `sess.run([train_op, global_step])`
+(/root/reference/scripts/runners.py:231-232) on one synthetic batch.  Rank 0 prints ONE JSON line.
+Workload = BASELINE.json configs[3]: GMVAE K=10, z=64, MLP 784-512-512, batch 16384 per GPU,
+data-parallel (weak scaling) with an NCCL gradient all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "cfg4": dict(model="gmvae", latent_size=64, hidden_sizes=[512, 512], mixture_components=10, batch=16384,
+                 desc="cfg4 (BASELINE.json configs[3]): GMVAE K=10 z=64 MLP 784-512-512 batch 16384/GPU"),
+    "cfg5": dict(model="gmvae", latent_size=128, hidden_sizes=[1024, 1024], mixture_components=50, batch=65536,
+                 desc="cfg5 (BASELINE.json configs[4]): GMVAE K=50 z=128 MLP 784-1024-1024 batch 65536/GPU"),
+    "cfg3": dict(model="gmvae", latent_size=64, hidden_sizes=[512, 512], mixture_components=10, batch=100,
+                 desc="cfg3 (BASELINE.json configs[2]): GMVAE K=10 z=64 MLP 784-512-512 batch 100"),
+}
+D = 784
+
+
+def flops_per_sample(w, objective="reference"):
+    """2*MACs of forward + weight-gradient + data-gradient GEMMs; the data gradient w.r.t. the
+    image is excluded (never needed).  Matches BASELINE.md section 3 (objective R)."""
+    H, Z, K = w["hidden_sizes"], w["latent_size"], w["mixture_components"]
+
+    def mlp(i, o):
+        sizes = [i] + H + [o]
+        return [(sizes[j], sizes[j + 1]) for j in range(len(sizes) - 1)]
+    fwd = dgrad = 0
+    nets = [("enc_y", mlp(D, K), False), ("enc_gmm", mlp(D + K, 2 * Z), True), ("prior", [(K, 2 * Z)], True),
+            ("dec", mlp(Z, D), True)] if w["model"] == "gmvae" else [("enc", mlp(D, 2 * Z), False), ("dec", mlp(Z, D), True)]
+    for name, layers, need_input_grad in nets:
+        for j, (i, o) in enumerate(layers):
+            fwd += i * o
+            if j > 0:
+                dgrad += i * o
+            elif need_input_grad:
+                dgrad += (i - D if name == "enc_gmm" else i) * o   # only the y / z columns need a data gradient
+    return 2 * (2 * fwd + dgrad)
+
+
+def tc_flops_per_sample(w):
+    """The part of flops_per_sample that runs on the tcgen05 path (every linear with in >= 32 and
+    out >= 32, engine.cu lin_fwd/lin_dgrad/lin_wgrad); the rest (K- or N = mixture components)
+    runs on the SIMT kernel."""
+    H, Z, K = w["hidden_sizes"], w["latent_size"], w["mixture_components"]
+
+    def mlp(i, o):
+        sizes = [i] + H + [o]
+        return [(sizes[j], sizes[j + 1]) for j in range(len(sizes) - 1)]
+    tot = 0
+    nets = [("enc_y", mlp(D, K)), ("enc_gmm", mlp(D, 2 * Z)), ("dec", mlp(Z, D))] if w["model"] == "gmvae" else \
+           [("enc", mlp(D, 2 * Z)), ("dec", mlp(Z, D))]
+    for name, layers in nets:
+        for j, (i, o) in enumerate(layers):
+            if i >= 32 and o >= 32:
+                tot += 2 * i * o + (i * o if (j > 0 or name == "dec") else 0)
+    return 2 * tot
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1346.3), d.get("hbm_gbs", 6533.2), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def synthetic_images(batch, seed):
+    """per-pixel rate p_d ~ U(0,1) drawn once; x = U(0,1) < p_d (bool)."""
+    g = torch.Generator().manual_seed(seed)
+    p = torch.rand(D, generator=g)
+    return (torch.rand(batch, D, generator=g) < p).to(torch.uint8)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_step_rate(w, sample_batch, steps, threads):
+    """The reference's training step restated on the CPU (oracle/, PyTorch fp32, autograd backward,
+    TF-form Adam) -- `kind: "port"`: TF 1.13 cannot be installed here."""
+    from oracle import gmvae_oracle as O
+    torch.set_num_threads(threads)
+    spec = O.Spec(w["model"], D, w["latent_size"], list(w["hidden_sizes"]), w["mixture_components"])
+    params = O.init_params(spec, dtype=torch.float32)
+    st = O.adam_init(params)
+    x, _, eps, u = O.synthetic_batch(spec, sample_batch)
+    O.train_step(spec, params, st, x, eps, u)       # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(spec, params, st, x, eps, u)
+    dt = time.perf_counter() - t0
+    return sample_batch * steps / dt, dt
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(w["batch"], 4096)
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_step_rate(w, sample, 1, cores)
+    rate, dt = cpu_step_rate(w, sample, max(args.steps, 1), cores)
+    line = {
+        "impl": "reference", "metric": "GMVAE train samples/sec (fwd+bwd+Adam)", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "objective": "reference (gmvae.py:238-267)", "note": "host CPU only; GPUs idle"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} samples/step x {args.steps} steps of the same model (restated reference graph on "
+                                   f"PyTorch-CPU fp32; TF 1.13 not installable)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def flush_l2(buf):
+    buf.add_(1)
+
+
+def run_gpu_arm(args, w):
+    import torch.distributed as dist
+    import gmvae_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or w["batch"]
+    eng = gmvae_b200.Engine(model=w["model"], data_size=D, latent_size=w["latent_size"], hidden_sizes=w["hidden_sizes"],
+                            mixture_components=w["mixture_components"], precision=args.precision, objective=args.objective,
+                            max_batch=B, device=local, seed=1234 + rank)
+    if world > 1:
+        eng.init_data_parallel()
+
+    x_host = synthetic_images(B, 1234 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    side = torch.cuda.Stream(dev)
+    l2_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput: graph replay of the whole step ----------------------------
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eng.train_step(x_dev)
+        if args.no_graph:
+            step = lambda: eng.train_step(x_dev)
+        else:
+            eng.capture_step(x_dev)
+            step = eng.replay
+        for _ in range(args.warmup):
+            step()
+        side.synchronize()
+        n0 = eng.launch_count()
+        eng.train_step(x_dev)
+        launches_per_step = eng.launch_count() - n0
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush_l2(l2_buf)                      # evict the previous step's tensors from L2 (untimed)
+            ev[i][0].record(side)
+            step()
+            ev[i][1].record(side)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        loss_terms = eng.loss_buf.cpu().tolist()
+
+        # ---- per-kernel-class device time: CUDA events after every launch of 3 eager steps --------
+        prof_steps = 3
+        eng.profile(True)
+        for _ in range(prof_steps):
+            flush_l2(l2_buf)
+            eng.train_step(x_dev)
+        side.synchronize()
+        prof = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] // prof_steps}
+                for k, v in eng.profile_read().items()}
+        eng.profile(False)
+
+        # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ----------------
+        copy_stream = torch.cuda.Stream(dev)
+        stage = [torch.empty_like(x_dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(args.steps + args.warmup, 4).pin_memory()
+
+        def e2e_loop(n, off):
+            for i in range(n):
+                s = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[s])
+                    stage[s].copy_(x_host, non_blocking=True)
+                    ready[s].record(copy_stream)
+                side.wait_event(ready[s])
+                x_dev.copy_(stage[s], non_blocking=True)
+                consumed[s].record(side)
+                step()
+                loss_host[off + i].copy_(eng.loss_buf, non_blocking=True)
+        for s in range(2):
+            consumed[s].record(side)
+        e2e_loop(args.warmup, 0)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(side)
+        e2e_loop(args.steps, args.warmup)
+        t1.record(side)
+        barrier()
+        e2e_ms = t0.elapsed_time(t1)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    fps = flops_per_sample(w, args.objective)
+    ms_per_step = dev_ms / args.steps
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    step_tf = (B * fps) / (ms_per_step * 1e-3) / 1e12
+    tc_ms = prof["tc_gemm_fwd_dgrad"]["ms_per_step"] + prof["tc_gemm_wgrad"]["ms_per_step"]
+    tc_launches = prof["tc_gemm_fwd_dgrad"]["launches_per_step"] + prof["tc_gemm_wgrad"]["launches_per_step"]
+    achieved_tf = (B * tc_flops_per_sample(w)) / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": "GMVAE train samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": w["desc"], "objective": args.objective, "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2": "L2 flushed (256 MB write) between timed steps", "graph": not args.no_graph,
+                   "noise": "drawn on device (Philox) each step", "loss_terms": loss_terms},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": 16,
+                "ms_per_step": e2e_ms / args.steps, "note": "pinned uint8 batch -> H2D (copy stream, double-buffered) -> graph -> D2H loss"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": None, "kernel": f"gemm_tc_kernel (tcgen05; {tc_launches} launches/step, {tc_ms:.3f} ms/step by CUDA events)",
+                     "peak_source": peak_src, "flop_per_sample": fps, "tc_flop_per_sample": tc_flops_per_sample(w),
+                     "whole_step_tflops": step_tf, "whole_step_frac": step_tf / peak_tf},
+        "kernel_profile": prof,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        sample = min(B, 4096)
+        rate, dt = cpu_step_rate(w, sample, 3, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} samples/step x 3 steps, restated reference graph on PyTorch-CPU fp32 ({dt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--objective", default="reference", choices=["reference", "marginal"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+    else:
+        run_gpu_arm(args, w)
+
+
+if __name__ == "__main__":
+    main()

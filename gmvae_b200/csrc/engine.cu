@@ -94,6 +94,9 @@ struct LinView {
 };
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8 };
+// kernel classes of the per-launch profile (gmvae_profile_read)
+enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
+       PC_COUNT = 7 };
 
 }  // namespace gmvae
 
@@ -119,6 +122,9 @@ struct gmvae_handle {
   DeviceState* state = nullptr;
   int64_t launches = 0;
   int debug_flags = 0;
+  // per-launch CUDA-event profile (off by default; bench.py turns it on for a few eager steps)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, int>> marks;
   // NCCL
   ncclComm_t comm = nullptr; int world = 1, rank = 0;
   // graph
@@ -247,10 +253,21 @@ static LinView view(const gmvae_handle* h, const Linear& l, int row0 = 0, int ro
   return v;
 }
 
+// An event after every launch; the time between consecutive events on the in-order stream is
+// that launch's duration (plus the launch gap).  PC_START marks carry no duration.
+static int profile_mark(gmvae_handle* h, cudaStream_t st, int cls) {
+  cudaEvent_t e;
+  GM_CHECK_CUDA(cudaEventCreate(&e));
+  GM_CHECK_CUDA(cudaEventRecord(e, st));
+  h->marks.emplace_back(e, cls);
+  return 0;
+}
+
 // ============================================================================ GEMM dispatch
-#define GM_LAUNCHED(h, st)                                                   \
+#define GM_LAUNCHED(h, st, cls)                                              \
   do {                                                                       \
     (h)->launches++;                                                         \
+    if ((h)->profiling) GM_TRY(profile_mark(h, st, cls));                    \
     if ((h)->debug_flags & DBG_SYNC_EACH) GM_CHECK_CUDA(cudaStreamSynchronize(st)); \
   } while (0)
 
@@ -263,7 +280,7 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
   if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N % 128 != 0 && N % 112 == 0) r = tc::launch_gemm_tc<112, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  if (r == 0) GM_LAUNCHED(h, st);
+  if (r == 0) GM_LAUNCHED(h, st, PC_TC_GEMM);
   return r;
 }
 
@@ -286,7 +303,7 @@ static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinVi
   }
   GM_REQUIRE(L2 == nullptr, "two-segment forward requires the tensor-core path");
   GM_CHECK_CUDA((launch_gemm_simt<TA, float, Epi>(A, lda, 1, L.w, L.ldw32, 1, M, L.out, L.in, 1, epi, st)));
-  GM_LAUNCHED(h, st);
+  GM_LAUNCHED(h, st, PC_SIMT_GEMM);
   return 0;
 }
 
@@ -302,7 +319,7 @@ static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const Li
     }
   }
   GM_CHECK_CUDA((launch_gemm_simt<TD, float, Epi>(dY, ldy, 1, L.w, 1, L.ldw32, M, L.in, L.out, 1, epi, st)));
-  GM_LAUNCHED(h, st);
+  GM_LAUNCHED(h, st, PC_SIMT_GEMM);
   return 0;
 }
 
@@ -322,14 +339,14 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
       int split = std::max(1, std::min(kb, (2 * 148 + tiles - 1) / tiles));
       int r = bn == 64 ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
                        : tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st);
-      if (r == 0) GM_LAUNCHED(h, st);
+      if (r == 0) GM_LAUNCHED(h, st, PC_TC_WGRAD);
       return r;
     }
   }
   const int tiles = ((L.in + SIMT_BM - 1) / SIMT_BM) * ((L.out + SIMT_BN - 1) / SIMT_BN);
   int split = std::max(1, std::min((M + 255) / 256, (4 * 148 + tiles - 1) / tiles));
   GM_CHECK_CUDA((launch_gemm_simt<TA, TD, EpiAtomicAdd>(A, 1, lda, dY, ldy, 1, L.in, L.out, M, split, epi, st)));
-  GM_LAUNCHED(h, st);
+  GM_LAUNCHED(h, st, PC_SIMT_GEMM);
   return 0;
 }
 
@@ -340,7 +357,7 @@ static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, fl
   dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
   colsum_kernel<T><<<grid, 256, 0, st>>>(dY, ldy, M, N, rows_per_block, db);
   GM_CHECK_CUDA(cudaGetLastError());
-  GM_LAUNCHED(h, st);
+  GM_LAUNCHED(h, st, PC_BIAS_GRAD);
   return 0;
 }
 
@@ -419,13 +436,14 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   const float inv_bg = 1.f / (float)Bg;
   const bool gm = c.model == GMVAE_MODEL_GMVAE;
   float* acc = h->grads + h->n_params;
+  if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
   GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
 
   A* x_act = h->buf<A>("x_act");
   {
     int64_t n = (int64_t)B * D;
     convert_x_kernel<A><<<(unsigned)((n / 16 + 255) / 256 + 1), 256, 0, st>>>(x_u8, x_act, n);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_MISC);
   }
   const float* eps = eps_in; const float* u = u_in;
   if (!eps || (gm && !u)) {
@@ -433,7 +451,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
     int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
     fill_noise_kernel<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(e, ne, uu, nu, h->state, (uint64_t)h->rank);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_MISC);
     if (!eps) eps = e;
     if (gm && !u) u = uu;
   }
@@ -463,7 +481,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? D : h->hidden[nl - 2], B, view(h, l), epi, st));
     }
     head_y_fwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, u, B, K, 1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
     // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
     {
       const Linear& l = h->prior_gmm.layers[0];
@@ -511,7 +529,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     int64_t n = (int64_t)B * Z;
     head_z_fwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, prior_mode, B, Z, c.raw_sigma_bias,
                                                                     c.sigma_min, inv_bg, z_act, z_f32, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
   float* dz_prior = h->buf<float>("dz_prior");
   if (prior_mode == 1) {
@@ -519,7 +537,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     gmp_prior_kernel<<<(B + warps - 1) / warps, warps * 32, warps * K * sizeof(float), st>>>(
         z_f32, h->params + h->loc_off, h->params + h->raw_scale_off, h->params + h->mix_off, B, K, Z, inv_bg, dz_prior,
         h->grads + h->loc_off, h->grads + h->raw_scale_off, h->grads + h->mix_off, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
   // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood
   GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Z, B, 0, st));
@@ -543,7 +561,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     int64_t n = (int64_t)B * Z;
     head_z_bwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, dz, dz_prior, prior_mode, B, Z,
                                                                     c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, d_prior_out);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
   GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, D, D, d_enc_out, 2 * Z, B, st)));
   if (gm) {
@@ -569,7 +587,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       GM_TRY((lin_dgrad<float>(h, d_prior_out, 2 * Z, B, Lp, e, st)));
     }
     head_y_bwd_kernel<0><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
     GM_TRY((mlp_backward<A, float>(h, h->encoder_y, ey, x_act, D, D, dlogits_y, K, B, st)));
   }
   return 0;
@@ -578,10 +596,10 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
 static int refresh_shadows(gmvae_handle* h, bool bump, cudaStream_t st) {
   if (h->shadow_tiles > 0) {
     refresh_shadows_kernel<<<h->shadow_tiles, dim3(32, 8), 0, st>>>(h->shadow_dev, (int)h->shadow_host.size(), h->state, bump ? 1 : 0);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
   } else if (bump) {
     bump_step_kernel<<<1, 1, 0, st>>>(h->state);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
   }
   return 0;
 }
@@ -706,7 +724,7 @@ int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
   GM_TRY(check_ready(h));
   GM_REQUIRE(loss_terms != nullptr, "null loss_terms");
   finalize_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->grads + h->n_params, loss_terms);
-  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, (cudaStream_t)stream);
+  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, (cudaStream_t)stream, PC_MISC);
   return 0;
 }
 
@@ -717,7 +735,7 @@ int gmvae_adam_step(gmvae_handle* h, void* stream) {
   int64_t n = h->n_params;
   adam_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, n, c.learning_rate,
                                                                   c.beta1, c.beta2, c.epsilon, h->state);
-  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st);
+  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
   return refresh_shadows(h, true, st);
 }
 
@@ -816,6 +834,29 @@ int gmvae_decode(gmvae_handle*, const float*, int, float*, void*) {
 int gmvae_prior_table(gmvae_handle*, float*, float*, void*) {
   set_error("gmvae_prior_table: not built yet");
   return -6;
+}
+
+int gmvae_profile_enable(gmvae_handle* h, int on) {
+  GM_REQUIRE(h, "null argument");
+  for (auto& m : h->marks) cudaEventDestroy(m.first);
+  h->marks.clear();
+  h->profiling = on != 0;
+  return 0;
+}
+int gmvae_profile_read(gmvae_handle* h, double* ms_by_class, int64_t* launches_by_class, int n_classes) {
+  GM_REQUIRE(h && ms_by_class && launches_by_class, "null argument");
+  GM_REQUIRE(n_classes >= PC_COUNT, "need room for 7 classes");
+  for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0; launches_by_class[i] = 0; }
+  if (h->marks.empty()) return 0;
+  GM_CHECK_CUDA(cudaEventSynchronize(h->marks.back().first));
+  for (size_t i = 1; i < h->marks.size(); ++i) {
+    int cls = h->marks[i].second;
+    if (cls < 0) continue;
+    float ms = 0.f;
+    GM_CHECK_CUDA(cudaEventElapsedTime(&ms, h->marks[i - 1].first, h->marks[i].first));
+    ms_by_class[cls] += ms; launches_by_class[cls] += 1;
+  }
+  return PC_COUNT;
 }
 
 // ---- kernel-level test hook ------------------------------------------------------------------

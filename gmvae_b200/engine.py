@@ -262,6 +262,16 @@ class Engine:
         dist.broadcast_object_list(obj, src=0)
         _lib.check(self.lib.gmvae_nccl_init(self._h, obj[0], self.world_size, self.rank), "gmvae_nccl_init")
 
+    PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc"]
+
+    def profile(self, on: bool):
+        _lib.check(self.lib.gmvae_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> Dict[str, dict]:
+        ms = (C.c_double * 8)(); n = (C.c_int64 * 8)()
+        self.lib.gmvae_profile_read(self._h, ms, n, 8)
+        return {name: {"ms": ms[i], "launches": int(n[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
+
     def debug_gemm(self, impl: int, A: torch.Tensor, B: torch.Tensor, transA=False, transB=False, split_k=1) -> torch.Tensor:
         """C = op(A) op(B) through the step's own GEMM kernels (impl 0 SIMT fp32, 1 tcgen05 bf16)."""
         A = A.to(self.device, torch.float32).contiguous(); B = B.to(self.device, torch.float32).contiguous()

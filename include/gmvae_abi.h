@@ -155,6 +155,13 @@ GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* 
 GMVAE_API int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K,
                      const float* A, const float* B, float* C, int split_k, void* stream);
 
+/* Per-launch profile: with profiling on, a CUDA event is recorded after every launch of the
+ * (eager) step; read() returns the summed device time and launch count per kernel class:
+ * 0 tcgen05 GEMM fwd/dgrad, 1 tcgen05 GEMM wgrad, 2 SIMT GEMM, 3 distribution heads,
+ * 4 bias gradients, 5 Adam + bf16 operand refresh, 6 misc (convert, noise, finalize). */
+GMVAE_API int gmvae_profile_enable(gmvae_handle* h, int on);
+GMVAE_API int gmvae_profile_read(gmvae_handle* h, double* ms_by_class, int64_t* launches_by_class, int n_classes);
+
 /* Number of kernels this library has launched on behalf of the handle (bench "gpu_launches"). */
 GMVAE_API int64_t gmvae_launch_count(const gmvae_handle* h);
 

@@ -111,12 +111,38 @@ def init_params(spec: Spec, seed: int = 2024, dtype=torch.float64) -> Dict[str, 
     return params
 
 
-def mlp(params: Dict[str, torch.Tensor], name: str, h: torch.Tensor, n_layers: int) -> torch.Tensor:
+class Exact:
+    """Rounding model of the arithmetic: the default is none (exact fp64/fp32 evaluation).
+    tests/helpers.py subclasses it to restate WHERE the bf16 CUDA path rounds (stored activations,
+    stored activation gradients, tensor-core weight operands), so that bf16 gradients can be
+    compared without the ReLU-mask flips that any reduced-precision forward pass produces."""
+
+    def act(self, t):            # a stored hidden activation (and its stored gradient)
+        return t
+
+    def fwd(self, t):            # stored in reduced precision in the forward pass only
+        return t
+
+    def grad(self, t):           # only the gradient flowing back through t is stored reduced
+        return t
+
+    def weight(self, name, w):   # GEMM weight operand
+        return w
+
+    def yin(self, t):            # the relaxed sample y as input of encoder_gmm
+        return t
+
+
+EXACT = Exact()
+
+
+def mlp(params: Dict[str, torch.Tensor], name: str, h: torch.Tensor, n_layers: int, q: Exact = EXACT) -> torch.Tensor:
     """snt.nets.MLP(activation=relu, activate_final=False): relu between layers only."""
     for i in range(n_layers):
-        h = h @ params[f"{name}_fcnet/linear_{i}/w"] + params[f"{name}_fcnet/linear_{i}/b"]
+        wn = f"{name}_fcnet/linear_{i}/w"
+        h = h @ q.weight(wn, params[wn]) + params[f"{name}_fcnet/linear_{i}/b"]
         if i != n_layers - 1:
-            h = torch.relu(h)
+            h = q.act(torch.relu(h))
     return h
 
 
@@ -155,7 +181,7 @@ def entropy(logits, targets):
 
 def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
                eps: torch.Tensor, u: Optional[torch.Tensor] = None,
-               objective: str = "reference", global_batch: Optional[int] = None) -> Dict[str, torch.Tensor]:
+               objective: str = "reference", global_batch: Optional[int] = None, q: Exact = EXACT) -> Dict[str, torch.Tensor]:
     """Forward pass.  Returns loss, nll, kl_div_z, nent (nent == 0 for VAE models) and a few
     intermediates used by the tests.  `global_batch` (default: len(x)) is the divisor of the
     batch means, so that shards of a data-parallel batch can be summed."""
@@ -166,9 +192,9 @@ def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
     L = len(spec.hidden_sizes) + 1
     out: Dict[str, torch.Tensor] = {}
     if spec.model in ("vae", "vae_gmp"):                                   # vae.py:167-185
-        mu_q, sg_q = normal_params(spec, mlp(params, "encoder", x, L))
+        mu_q, sg_q = normal_params(spec, q.grad(mlp(params, "encoder", x, L, q)))
         z = mu_q + sg_q * eps.to(dt)
-        logits = mlp(params, "decoder", z, L) + spec.gen_bias_init
+        logits = q.grad(mlp(params, "decoder", q.fwd(z), L, q)) + spec.gen_bias_init
         nll = -bernoulli_log_prob(x, logits).sum() / Bg
         logq = mvn_diag_log_prob(z, mu_q, sg_q)
         if spec.model == "vae":                                           # vae.py:247-250
@@ -183,15 +209,15 @@ def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
     if spec.model != "gmvae":
         raise ValueError(spec.model)
     K, Z = spec.mixture_components, spec.latent_size
-    ly = mlp(params, "encoder_y", x, L)                                    # gmvae.py:238
+    ly = mlp(params, "encoder_y", x, L, q)                                 # gmvae.py:238
     py = torch.softmax(ly, -1)
     nent = -entropy(ly, py).sum() / Bg                                     # gmvae.py:262-263
     if objective == "reference":
         y = gumbel_softmax_sample(ly, u.to(dt), spec.temperature)          # gmvae.py:240
-        mu_p, sg_p = normal_params(spec, mlp(params, "prior_gmm", y, 1))   # gmvae.py:243
-        mu_q, sg_q = normal_params(spec, mlp(params, "encoder_gmm", torch.cat([x, y], 1), L))  # :246
+        mu_p, sg_p = normal_params(spec, mlp(params, "prior_gmm", y, 1, q))   # gmvae.py:243
+        mu_q, sg_q = normal_params(spec, q.grad(mlp(params, "encoder_gmm", torch.cat([x, q.yin(y)], 1), L, q)))  # :246
         z = mu_q + sg_q * eps.to(dt)                                       # gmvae.py:248
-        logits = mlp(params, "decoder", z, L) + spec.gen_bias_init         # gmvae.py:251
+        logits = q.grad(mlp(params, "decoder", q.fwd(z), L, q)) + spec.gen_bias_init   # gmvae.py:251
         nll = -bernoulli_log_prob(x, logits).sum() / Bg                    # gmvae.py:254
         kl = (mvn_diag_log_prob(z, mu_q, sg_q) - mvn_diag_log_prob(z, mu_p, sg_p)).sum() / Bg  # :258
         out.update(y=y, z=z, logits_x=logits)
@@ -217,10 +243,10 @@ def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
     return out
 
 
-def loss_and_grads(spec, params, x, eps, u=None, objective="reference", global_batch=None):
+def loss_and_grads(spec, params, x, eps, u=None, objective="reference", global_batch=None, q: Exact = EXACT):
     """opt.compute_gradients(loss, tf.trainable_variables()) (runners.py:182) by autograd."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    terms = loss_terms(spec, leaf, x, eps, u, objective, global_batch)
+    terms = loss_terms(spec, leaf, x, eps, u, objective, global_batch, q)
     names = list(leaf)
     gs = torch.autograd.grad(terms["loss"], [leaf[n] for n in names], allow_unused=True)
     grads = {n: (g if g is not None else torch.zeros_like(leaf[n])) for n, g in zip(names, gs)}

@@ -55,11 +55,13 @@ def grad_errors(engine, grads_ref):
     return out
 
 
-def run_parity(cfg, precision, seed=2024):
+def run_parity(cfg, precision, seed=2024, rounding_model=None):
+    """Returns (loss-term errors, per-tensor gradient errors) of the CUDA step against the oracle.
+    With `rounding_model` the oracle restates the bf16 storage points of the CUDA path."""
     spec = make_spec(cfg)
     params = perturbed_params(spec, seed)
     x, labels, eps, u = O.synthetic_batch(spec, cfg["batch"])
-    terms_ref, grads_ref = O.loss_and_grads(spec, params, x, eps, u)
+    terms_ref, grads_ref = O.loss_and_grads(spec, params, x, eps, u, q=rounding_model or O.EXACT)
     eng = make_engine(cfg, precision)
     eng.set_parameters(params)
     loss = eng.forward_backward(x, eps=eps, gumbel_u=u)
@@ -71,3 +73,61 @@ def run_parity(cfg, precision, seed=2024):
     gerr = grad_errors(eng, grads_ref)
     eng.close()
     return terr, gerr
+
+
+# --------------------------------------------------------------------------- bf16 rounding model
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class Bf16Model(O.Exact):
+    """Where the bf16 CUDA path stores reduced precision (DESIGN.md "Precision"): hidden
+    activations and their gradients, z as the decoder's input, the gradients w.r.t. the decoder
+    logits and the encoder's [mu|raw] output, and -- when the tensor-core path is on -- the
+    weight operands of every GEMM with in >= 32 and out >= 32 (engine.cu lin_fwd / lin_dgrad)."""
+
+    def __init__(self, tensor_core_weights=True):
+        self.tcw = tensor_core_weights
+
+    def act(self, t):
+        return _RoundBoth.apply(t)
+
+    def fwd(self, t):
+        return _RoundFwd.apply(t)
+
+    def grad(self, t):
+        return _RoundGrad.apply(t)
+
+    def weight(self, name, w):
+        if self.tcw and w.shape[0] >= 32 and w.shape[1] >= 32:
+            return _RoundFwd.apply(w)
+        return w
+
+    def yin(self, t):            # y is the bf16 operand of the second K segment (tensor-core path)
+        return _RoundFwd.apply(t) if self.tcw else t
