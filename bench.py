@@ -153,7 +153,11 @@ def run_reference_arm(args, w):
     sample = min(w["batch"], 4096)
     for _ in range(max(args.warmup, 1) - 1):
         cpu_step_rate(w, sample, 1, cores)
-    rate, dt = cpu_step_rate(w, sample, max(args.steps, 1), cores)
+    _, dt1 = cpu_step_rate(w, sample, 2, cores)
+    # bounded: at most args.steps steps and at most ~60 s of CPU work
+    nsteps = max(1, min(args.steps, int(60.0 / max(dt1 / 2, 1e-4))))
+    rate, dt = cpu_step_rate(w, sample, nsteps, cores)
+    args.steps = nsteps
     line = {
         "impl": "reference", "metric": "GMVAE train samples/sec (fwd+bwd+Adam)", "value": rate, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
@@ -312,9 +316,11 @@ def run_gpu_arm(args, w):
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         sample = min(B, 4096)
-        rate, dt = cpu_step_rate(w, sample, 3, cores)
+        _, dt1 = cpu_step_rate(w, sample, 2, cores)
+        n = max(3, min(2000, int(12.0 / max(dt1 / 2, 1e-4))))         # ~12 s of CPU work
+        rate, dt = cpu_step_rate(w, sample, n, cores)
         line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} samples/step x 3 steps, restated reference graph on PyTorch-CPU fp32 ({dt:.1f} s)"}
+                                "sample": f"{sample} samples/step x {n} steps, restated reference graph on PyTorch-CPU fp32 ({dt:.1f} s)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -323,8 +329,8 @@ def run_gpu_arm(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

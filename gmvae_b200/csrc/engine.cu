@@ -224,9 +224,9 @@ static int plan(gmvae_handle* h) {
     plan_buf(h, "y_f32", B * K * 4);
     plan_buf(h, "y_act", B * Kp * asz);
     plan_buf(h, "prior_out", B * 2 * Z * 4);
-    plan_buf(h, "d_prior_out", B * 2 * Z * 4);
+    plan_buf(h, "d_prior_out", B * 2 * Z * asz);
     plan_buf(h, "dy", B * K * 4);
-    plan_buf(h, "dlogits_y", B * K * 4);
+    plan_buf(h, "dlogits_y", B * Kp * asz);
     plan_buf(h, "pre_y", B * (size_t)(h->hidden.empty() ? 2 * Z : h->hidden[0]) * 4);
   }
   if (c.model == GMVAE_MODEL_VAE_GMP) {
@@ -272,12 +272,16 @@ static int profile_mark(gmvae_handle* h, cudaStream_t st, int cls) {
   } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// extent of a dimension whose buffer is zero-padded to a multiple of 8 elements (16 bytes)
+static inline int kpad(int k, int64_t ld) { return (int)std::min<int64_t>(ld, round_up(k, 8)); }
 
 template <class Epi>
 static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Operand& B, const tc::Operand* A2,
                           const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
   int r;
-  if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  if (N <= 16) r = tc::launch_gemm_tc<16, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else if (N <= 32) r = tc::launch_gemm_tc<32, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N % 128 != 0 && N % 112 == 0) r = tc::launch_gemm_tc<112, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   if (r == 0) GM_LAUNCHED(h, st, PC_TC_GEMM);
@@ -289,13 +293,14 @@ template <typename TA, class Epi>
 static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinView& L, const Epi& epi, cudaStream_t st,
                    const TA* A2 = nullptr, int64_t lda2 = 0, const LinView* L2 = nullptr) {
   if constexpr (std::is_same<TA, bf16>::value) {
-    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && L.in >= 32 && L.out >= 32 && lda % 8 == 0 &&
-              aligned16(A) && aligned16(L.wt_bf16);
+    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && lda % 8 == 0 && aligned16(A) &&
+              aligned16(L.wt_bf16);
     if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->wt_bf16);
     if (ok) {
-      tc::Operand a{A, lda, M, L.in}, b{L.wt_bf16, L.ld_wt, L.out, L.in};
+      // K extents are rounded up to the (zero-filled) 16-byte padding of the buffers.
+      tc::Operand a{A, lda, M, kpad(L.in, lda)}, b{L.wt_bf16, L.ld_wt, L.out, kpad(L.in, L.ld_wt)};
       if (L2) {
-        tc::Operand a2{A2, lda2, M, L2->in}, b2{L2->wt_bf16, L2->ld_wt, L2->out, L2->in};
+        tc::Operand a2{A2, lda2, M, kpad(L2->in, lda2)}, b2{L2->wt_bf16, L2->ld_wt, L2->out, kpad(L2->in, L2->ld_wt)};
         return tc_dispatch_kk(h, a, b, &a2, &b2, M, L.out, epi, st);
       }
       return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.out, epi, st);
@@ -311,10 +316,10 @@ static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinVi
 template <typename TD, class Epi>
 static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const LinView& L, const Epi& epi, cudaStream_t st) {
   if constexpr (std::is_same<TD, bf16>::value) {
-    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && L.in >= 32 && L.out >= 32 && ldy % 8 == 0 &&
-              aligned16(dY) && aligned16(L.w_bf16);
+    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && ldy % 8 == 0 && aligned16(dY) &&
+              aligned16(L.w_bf16);
     if (ok) {
-      tc::Operand a{dY, ldy, M, L.out}, b{L.w_bf16, L.ld_w, L.in, L.out};
+      tc::Operand a{dY, ldy, M, kpad(L.out, ldy)}, b{L.w_bf16, L.ld_w, L.in, kpad(L.out, L.ld_w)};
       return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.in, epi, st);
     }
   }
@@ -329,10 +334,10 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
                      cudaStream_t st) {
   EpiAtomicAdd epi{L.dw, (int64_t)L.ldw32};
   if constexpr (std::is_same<TA, bf16>::value && std::is_same<TD, bf16>::value) {
-    bool ok = h->bf16_mode() && !(h->debug_flags & (DBG_NO_TC | DBG_NO_TC_WGRAD)) && L.in >= 32 && L.out >= 32 && lda % 8 == 0 &&
-              ldy % 8 == 0 && aligned16(A) && aligned16(dY);
+    bool ok = h->bf16_mode() && !(h->debug_flags & (DBG_NO_TC | DBG_NO_TC_WGRAD)) && lda % 8 == 0 && ldy % 8 == 0 &&
+              aligned16(A) && aligned16(dY);
     if (ok) {
-      tc::Operand a{A, lda, L.in, M}, b{dY, ldy, L.out, M};
+      tc::Operand a{A, lda, kpad(L.in, lda), M}, b{dY, ldy, kpad(L.out, ldy), M};
       const int bn = L.out <= 64 ? 64 : 128;
       const int tiles = ((L.in + 127) / 128) * ((L.out + bn - 1) / bn);
       const int kb = (M + tc::BLOCK_K - 1) / tc::BLOCK_K;
@@ -352,9 +357,10 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
 
 template <typename T>
 static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, float* db, cudaStream_t st) {
-  int rows_per_block = std::max(64, (M + 147) / 148);
+  const int col_blocks = (N + 255) / 256;
+  int rows_per_block = std::max(64, (M * col_blocks + 2 * 148 - 1) / (2 * 148));
   rows_per_block = round_up(rows_per_block, 8);
-  dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
+  dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
   colsum_kernel<T><<<grid, 256, 0, st>>>(dY, ldy, M, N, rows_per_block, db);
   GM_CHECK_CUDA(cudaGetLastError());
   GM_LAUNCHED(h, st, PC_BIAS_GRAD);
@@ -486,7 +492,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     {
       const Linear& l = h->prior_gmm.layers[0];
       EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 0, 1.f};
-      GM_TRY(lin_fwd<float>(h, y_f32, K, B, view(h, l), epi, st));
+      GM_TRY(lin_fwd<A>(h, y_act, Kp, B, view(h, l), epi, st));
     }
     // q(z|x,y) layer 0: [x,y] W = x W[:D] + y W[D:]  (no concat, base.py:66)
     LinView Lx = view(h, enc_l0, 0, D), Ly = view(h, enc_l0, D, K);
@@ -504,7 +510,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     } else {
       float* pre = h->buf<float>("pre_y");
       EpiStore<float> e0{pre, (int64_t)enc_l0.out, Lx.b, nullptr, 0, 0, 0, 1.f};
-      GM_TRY(lin_fwd<float>(h, y_f32, K, B, Ly, e0, st));
+      GM_TRY(lin_fwd<A>(h, y_act, Kp, B, Ly, e0, st));
       if (last0) {
         EpiStore<float> epi{enc_out, (int64_t)2 * Z, nullptr, pre, (int64_t)enc_l0.out, 0, 0, 1.f};
         GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st));
@@ -556,7 +562,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, D, B, view(h, l0), epi, st)));
     else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], l0.out, B, view(h, l0), epi, st)));
   }
-  float* d_prior_out = h->buf<float>("d_prior_out");
+  A* d_prior_out = h->buf<A>("d_prior_out");
   {
     int64_t n = (int64_t)B * Z;
     head_z_bwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, dz, dz_prior, prior_mode, B, Z,
@@ -565,15 +571,15 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   }
   GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, D, D, d_enc_out, 2 * Z, B, st)));
   if (gm) {
-    float* dy = h->buf<float>("dy"); float* dlogits_y = h->buf<float>("dlogits_y");
+    float* dy = h->buf<float>("dy"); A* dlogits_y = h->buf<A>("dlogits_y");
     LinView Ly = view(h, enc_l0, D, K);
     // y-columns of encoder_gmm layer 0: dW[D:] = y^T dh0 ; dy = dh0 W[D:]^T
     if (nl == 1) {
-      GM_TRY((lin_wgrad<float, A>(h, y_f32, K, d_enc_out, 2 * Z, B, Ly, st)));
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_enc_out, 2 * Z, B, Ly, st)));
       EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, d_enc_out, 2 * Z, B, Ly, e, st)));
     } else {
-      GM_TRY((lin_wgrad<float, A>(h, y_f32, K, enc.dhid[0], enc_l0.out, B, Ly, st)));
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, enc.dhid[0], enc_l0.out, B, Ly, st)));
       EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, enc.dhid[0], enc_l0.out, B, Ly, e, st)));
     }
@@ -581,14 +587,14 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     {
       const Linear& l = h->prior_gmm.layers[0];
       LinView Lp = view(h, l);
-      GM_TRY((lin_wgrad<float, float>(h, y_f32, K, d_prior_out, 2 * Z, B, Lp, st)));
-      GM_TRY(bias_grad<float>(h, d_prior_out, 2 * Z, B, 2 * Z, Lp.db, st));
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, 2 * Z, B, Lp, st)));
+      GM_TRY(bias_grad<A>(h, d_prior_out, 2 * Z, B, 2 * Z, Lp.db, st));
       EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1, 1.f};
-      GM_TRY((lin_dgrad<float>(h, d_prior_out, 2 * Z, B, Lp, e, st)));
+      GM_TRY((lin_dgrad<A>(h, d_prior_out, 2 * Z, B, Lp, e, st)));
     }
-    head_y_bwd_kernel<0><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y);
+    head_y_bwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
-    GM_TRY((mlp_backward<A, float>(h, h->encoder_y, ey, x_act, D, D, dlogits_y, K, B, st)));
+    GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, D, D, dlogits_y, Kp, B, st)));
   }
   return 0;
 }

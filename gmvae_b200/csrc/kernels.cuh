@@ -3,6 +3,7 @@
 // mixture prior), bias gradients, TF-form Adam and the bf16 operand refresh.
 #pragma once
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace gmvae {
 
@@ -21,8 +22,13 @@ __global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ 
   if (i + 16 <= n) {
     uint4 t = *reinterpret_cast<const uint4*>(x + i);
     const uint8_t* p = reinterpret_cast<const uint8_t*>(&t);
+    __align__(16) T v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) out[i + j] = from_f32<T>((float)p[j]);
+    for (int j = 0; j < 16; ++j) v[j] = from_f32<T>((float)p[j]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i);            // n*sizeof(T) stays 16-byte aligned
+    const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int j = 0; j < (int)(16 * sizeof(T) / 16); ++j) dst[j] = src[j];
   } else {
     for (int64_t j = i; j < n; ++j) out[j] = from_f32<T>((float)x[j]);
   }
@@ -110,10 +116,10 @@ __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float*
 
 // ---- q(y|x) head, backward --------------------------------------------------------------------
 // dl = softmax-Jacobian((l+g)/T)^T dy / T  +  d nent/dl,   d nent/dl_j = p_j (log p_j - sum p log p)/B
-template <int DUMMY = 0>
+template <typename ActT>
 __global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y_f32,
                                   const float* __restrict__ dy, int B, int K, float inv_T, float inv_bg,
-                                  float* __restrict__ dlogits) {
+                                  ActT* __restrict__ dlogits, int ld_out) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -148,7 +154,9 @@ __global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float*
     int k = lane + 32 * i;
     if (k < K) {
       float lp = l[i] - lse;
-      dlogits[(int64_t)row * K + k] = y[i] * (g[i] - ydy) * inv_T + expf(lp) * (lp - plogp) * inv_bg;
+      dlogits[(int64_t)row * ld_out + k] = from_f32<ActT>(y[i] * (g[i] - ydy) * inv_T + expf(lp) * (lp - plogp) * inv_bg);
+    } else if (k < ld_out) {
+      dlogits[(int64_t)row * ld_out + k] = from_f32<ActT>(0.f);
     }
   }
 }
@@ -200,7 +208,7 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
                                   const float* __restrict__ prior_out, const float* __restrict__ dz_dec,
                                   const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c,
                                   float sigma_min, float inv_bg, ActT* __restrict__ d_enc_out,
-                                  float* __restrict__ d_prior_out) {
+                                  ActT* __restrict__ d_prior_out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Z) return;
   int b = (int)(i / Z), j = (int)(i % Z);
@@ -222,8 +230,8 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
     float isp2 = 1.f / (sp * sp);
     dz += d * isp2 * inv_bg;
     float dsp = (1.f / sp - d * d * isp2 / sp) * inv_bg;
-    d_prior_out[(int64_t)b * 2 * Z + j] = -d * isp2 * inv_bg;
-    d_prior_out[(int64_t)b * 2 * Z + Z + j] = spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f;
+    d_prior_out[(int64_t)b * 2 * Z + j] = from_f32<ActT>(-d * isp2 * inv_bg);
+    d_prior_out[(int64_t)b * 2 * Z + Z + j] = from_f32<ActT>(spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f);
   }
   float dsg = dz * e - inv_bg / sg;
   d_enc_out[(int64_t)b * 2 * Z + j] = from_f32<ActT>(dz);
@@ -292,23 +300,37 @@ __global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __res
 }
 
 // ---- bias gradients: db[n] += sum_m dY[m,n] -----------------------------------------------------
+// Each thread owns 8 consecutive columns (one 16-byte load per row for bf16); a block covers
+// 256 columns x `rows_per_block` rows with 8 row-lanes, reduced through shared memory.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, int M, int N, int rows_per_block, float* __restrict__ db) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[8][32][9];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
+  const int n0 = blockIdx.x * 256 + tx * 8;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
-  float s = 0.f;
-  if (n < N)
-    for (int r = r0 + ty; r < r1; r += 8) s += to_f32<T>(dY[(int64_t)r * ld + n]);
-  sm[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0) {
+  float s[8];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) s += sm[i][tx];
-    if (n < N) atomicAdd(db + n, s);
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (n0 < N) {
+    const int nv = min(8, N - n0);
+    for (int r = r0 + ty; r < r1; r += 8) {
+      float v[8];
+      load_frag<8>(dY + (int64_t)r * ld + n0, v, nv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ty][tx][j] = s[j];
+  __syncthreads();
+  // 256 threads: thread t sums column t of the block over the 8 row-lanes
+  const int c = threadIdx.x, cx = c >> 3, cj = c & 7;
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sm[i][cx][cj];
+  const int n = blockIdx.x * 256 + c;
+  if (n < N && t != 0.f) atomicAdd(db + n, t);
 }
 
 // ---- loss terms ---------------------------------------------------------------------------------

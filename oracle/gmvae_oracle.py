@@ -209,12 +209,12 @@ def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
     if spec.model != "gmvae":
         raise ValueError(spec.model)
     K, Z = spec.mixture_components, spec.latent_size
-    ly = mlp(params, "encoder_y", x, L, q)                                 # gmvae.py:238
+    ly = q.grad(mlp(params, "encoder_y", x, L, q))                         # gmvae.py:238
     py = torch.softmax(ly, -1)
     nent = -entropy(ly, py).sum() / Bg                                     # gmvae.py:262-263
     if objective == "reference":
         y = gumbel_softmax_sample(ly, u.to(dt), spec.temperature)          # gmvae.py:240
-        mu_p, sg_p = normal_params(spec, mlp(params, "prior_gmm", y, 1, q))   # gmvae.py:243
+        mu_p, sg_p = normal_params(spec, q.grad(mlp(params, "prior_gmm", q.yin(y), 1, q)))   # gmvae.py:243
         mu_q, sg_q = normal_params(spec, q.grad(mlp(params, "encoder_gmm", torch.cat([x, q.yin(y)], 1), L, q)))  # :246
         z = mu_q + sg_q * eps.to(dt)                                       # gmvae.py:248
         logits = q.grad(mlp(params, "decoder", q.fwd(z), L, q)) + spec.gen_bias_init   # gmvae.py:251

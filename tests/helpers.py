@@ -108,9 +108,9 @@ class _RoundGrad(torch.autograd.Function):
 
 class Bf16Model(O.Exact):
     """Where the bf16 CUDA path stores reduced precision (DESIGN.md "Precision"): hidden
-    activations and their gradients, z as the decoder's input, the gradients w.r.t. the decoder
-    logits and the encoder's [mu|raw] output, and -- when the tensor-core path is on -- the
-    weight operands of every GEMM with in >= 32 and out >= 32 (engine.cu lin_fwd / lin_dgrad)."""
+    activations and their gradients, z as the decoder's input, y as a GEMM operand, the gradients
+    w.r.t. the decoder logits, the encoders' outputs and the prior's output, and -- when the
+    tensor-core path is on -- the weight operand of every GEMM (engine.cu lin_fwd / lin_dgrad)."""
 
     def __init__(self, tensor_core_weights=True):
         self.tcw = tensor_core_weights
@@ -125,9 +125,7 @@ class Bf16Model(O.Exact):
         return _RoundGrad.apply(t)
 
     def weight(self, name, w):
-        if self.tcw and w.shape[0] >= 32 and w.shape[1] >= 32:
-            return _RoundFwd.apply(w)
-        return w
+        return _RoundFwd.apply(w) if self.tcw else w
 
     def yin(self, t):            # y is the bf16 operand of the second K segment (tensor-core path)
         return _RoundFwd.apply(t) if self.tcw else t
