@@ -43,6 +43,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
                    uint32_t box_inner, uint32_t box_outer) {
   typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> Key;
@@ -93,7 +104,7 @@ struct LinView {
   const bf16* wt_bf16; int ld_wt;   // [out, ld_wt], already offset to column row0
 };
 
-enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8 };
+enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32 };
 // kernel classes of the per-launch profile (gmvae_profile_read)
 enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
        PC_COUNT = 7 };
@@ -275,6 +286,17 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // extent of a dimension whose buffer is zero-padded to a multiple of 8 elements (16 bytes)
 static inline int kpad(int k, int64_t ld) { return (int)std::min<int64_t>(ld, round_up(k, 8)); }
 
+template <typename TA>
+static bool tc_ok_fwd(const gmvae_handle* h, const TA* A, int64_t lda, const LinView& L) {
+  return std::is_same<TA, bf16>::value && h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && lda % 8 == 0 &&
+         aligned16(A) && aligned16(L.wt_bf16);
+}
+template <typename TD>
+static bool tc_ok_dgrad(const gmvae_handle* h, const TD* dY, int64_t ldy, const LinView& L) {
+  return std::is_same<TD, bf16>::value && h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && ldy % 8 == 0 &&
+         aligned16(dY) && aligned16(L.w_bf16);
+}
+
 template <class Epi>
 static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Operand& B, const tc::Operand* A2,
                           const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
@@ -283,7 +305,8 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
   else if (N <= 32) r = tc::launch_gemm_tc<32, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N % 128 != 0 && N % 112 == 0) r = tc::launch_gemm_tc<112, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else if (N <= 128 || (h->debug_flags & DBG_BN128)) r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  else r = tc::launch_gemm_tc<256, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   if (r == 0) GM_LAUNCHED(h, st, PC_TC_GEMM);
   return r;
 }
@@ -293,8 +316,7 @@ template <typename TA, class Epi>
 static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinView& L, const Epi& epi, cudaStream_t st,
                    const TA* A2 = nullptr, int64_t lda2 = 0, const LinView* L2 = nullptr) {
   if constexpr (std::is_same<TA, bf16>::value) {
-    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && lda % 8 == 0 && aligned16(A) &&
-              aligned16(L.wt_bf16);
+    bool ok = tc_ok_fwd<TA>(h, A, lda, L);
     if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->wt_bf16);
     if (ok) {
       // K extents are rounded up to the (zero-filled) 16-byte padding of the buffers.
@@ -316,8 +338,7 @@ static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinVi
 template <typename TD, class Epi>
 static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const LinView& L, const Epi& epi, cudaStream_t st) {
   if constexpr (std::is_same<TD, bf16>::value) {
-    bool ok = h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && ldy % 8 == 0 && aligned16(dY) &&
-              aligned16(L.w_bf16);
+    bool ok = tc_ok_dgrad<TD>(h, dY, ldy, L);
     if (ok) {
       tc::Operand a{dY, ldy, M, kpad(L.out, ldy)}, b{L.w_bf16, L.ld_w, L.in, kpad(L.out, L.ld_w)};
       return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.in, epi, st);
@@ -338,12 +359,15 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
               aligned16(A) && aligned16(dY);
     if (ok) {
       tc::Operand a{A, lda, kpad(L.in, lda), M}, b{dY, ldy, kpad(L.out, ldy), M};
-      const int bn = L.out <= 64 ? 64 : 128;
+      const int bn = L.out <= 64 ? 64 : (L.out <= 128 || (h->debug_flags & DBG_BN128)) ? 128 : 256;
       const int tiles = ((L.in + 127) / 128) * ((L.out + bn - 1) / bn);
       const int kb = (M + tc::BLOCK_K - 1) / tc::BLOCK_K;
-      int split = std::max(1, std::min(kb, (2 * 148 + tiles - 1) / tiles));
-      int r = bn == 64 ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
-                       : tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st);
+      // one wave of persistent CTAs: split the batch so that tiles * split ~ number of SMs,
+      // keeping at least 4 k-blocks (256 samples) per split
+      int split = std::max(1, std::min(std::max(1, kb / 4), tc::num_sms() / tiles));
+      int r = bn == 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
+              : bn == 128 ? tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
+                          : tc::launch_gemm_tc<256, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st);
       if (r == 0) GM_LAUNCHED(h, st, PC_TC_WGRAD);
       return r;
     }
@@ -401,8 +425,10 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
 // `in0_cols` = how many leading rows of W_0 multiply `in0` (encoder_gmm: D of D+K).
 template <typename A, typename TD>
 static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols,
-                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st) {
+                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false) {
   const int nl = (int)m.layers.size();
+  const bool fuse = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+  bool bias_done = dout_bias_done;   // bias gradient of the layer whose output gradient we hold
   // last layer
   {
     const Linear& l = m.layers[nl - 1];
@@ -411,10 +437,14 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
     const A* in = first ? in0 : b.hid[nl - 2];
     int64_t ld = first ? ld0 : m.layers[nl - 2].out;
     GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
-    GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
+    if (!bias_done) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
     if (!first) {
-      EpiReluMask<A, A> epi{b.dhid[nl - 2], (int64_t)m.layers[nl - 2].out, b.hid[nl - 2], (int64_t)m.layers[nl - 2].out};
-      GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, view(h, l), epi, st)));
+      LinView Lf = view(h, l);
+      // the tensor-core epilogue also reduces the columns of what it stores = bias gradient of layer nl-2
+      float* cs = (fuse && tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf)) ? h->grads + m.layers[nl - 2].b_off : nullptr;
+      EpiReluMask<A, A> epi{b.dhid[nl - 2], (int64_t)m.layers[nl - 2].out, b.hid[nl - 2], (int64_t)m.layers[nl - 2].out, cs};
+      GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
+      bias_done = cs != nullptr;
     }
   }
   for (int i = nl - 2; i >= 0; --i) {
@@ -424,10 +454,14 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
     const A* in = first ? in0 : b.hid[i - 1];
     int64_t ld = first ? ld0 : m.layers[i - 1].out;
     GM_TRY((lin_wgrad<A, A>(h, in, ld, b.dhid[i], l.out, M, L, st)));
-    GM_TRY(bias_grad<A>(h, b.dhid[i], l.out, M, l.out, L.db, st));
+    if (!bias_done) GM_TRY(bias_grad<A>(h, b.dhid[i], l.out, M, l.out, L.db, st));
+    bias_done = false;
     if (!first) {
-      EpiReluMask<A, A> epi{b.dhid[i - 1], (int64_t)m.layers[i - 1].out, b.hid[i - 1], (int64_t)m.layers[i - 1].out};
-      GM_TRY((lin_dgrad<A>(h, b.dhid[i], l.out, M, view(h, l), epi, st)));
+      LinView Lf = view(h, l);
+      float* cs = (fuse && tc_ok_dgrad<A>(h, b.dhid[i], l.out, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
+      EpiReluMask<A, A> epi{b.dhid[i - 1], (int64_t)m.layers[i - 1].out, b.hid[i - 1], (int64_t)m.layers[i - 1].out, cs};
+      GM_TRY((lin_dgrad<A>(h, b.dhid[i], l.out, M, Lf, epi, st)));
+      bias_done = cs != nullptr;
     }
   }
   return 0;
@@ -545,17 +579,22 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
         h->grads + h->loc_off, h->grads + h->raw_scale_off, h->grads + h->mix_off, acc);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
+  bool dec_bias_fused = false;
   // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood
   GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Z, B, 0, st));
   {
     const Linear& l = h->decoder.layers[nl - 1];
+    const A* in = nl == 1 ? z_act : dec.hid[nl - 2];
+    const int64_t ldin = nl == 1 ? Z : h->hidden[nl - 2];
+    LinView Ld = view(h, l);
+    dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, in, ldin, Ld);
     EpiBCE<A> epi{dlogits_x, (int64_t)D, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, nullptr,
-                  acc + ACC_NLL, inv_bg, 0.f};
-    GM_TRY(lin_fwd<A>(h, nl == 1 ? z_act : dec.hid[nl - 2], nl == 1 ? Z : h->hidden[nl - 2], B, view(h, l), epi, st));
+                  acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
+    GM_TRY(lin_fwd<A>(h, in, ldin, B, Ld, epi, st));
   }
 
   // -------------------------------------------------------------------------- backward
-  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Z, Z, dlogits_x, D, B, st)));
+  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Z, Z, dlogits_x, D, B, st, dec_bias_fused)));
   {  // dz = d(first decoder layer input)
     const Linear& l0 = h->decoder.layers[0];
     EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 0, 1.f};
@@ -898,8 +937,9 @@ int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, i
     r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, epi, st);
   } else {
     tc::Operand a{a16, M, M, K}, b{b16, N, N, K};
-    r = N <= 64 ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
-                : tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st);
+    r = N <= 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
+        : N <= 128 ? tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
+                   : tc::launch_gemm_tc<256, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(a16); cudaFree(b16);

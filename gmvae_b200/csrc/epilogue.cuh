@@ -98,6 +98,81 @@ __device__ __forceinline__ void load_frag(const uint8_t* src, float* v, int nval
   }
 }
 
+// ---- per-column sum over the 32 rows a warp holds (lane = row): recursive halving, 31 shuffles.
+// On return lane l holds the sum of column (l % NV) ... for NV == 32 exactly column l; for
+// NV == 16 lanes l and l+16 both hold column l % 16 partial sums of their half-warps.
+template <int NV>
+__device__ __forceinline__ float warp_colsum(const float* v, int lane) {
+  float a[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = v[i];
+  // step s halves the number of live columns per lane: keep the half selected by lane bit
+  if constexpr (NV >= 32) {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float send = up ? a[i] : a[i + 16];
+      float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      a[i] = (up ? a[i + 16] : a[i]) + recv;
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = up ? a[i] : a[i + 8];
+      float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      a[i] = (up ? a[i + 8] : a[i]) + recv;
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = up ? a[i] : a[i + 4];
+      float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      a[i] = (up ? a[i + 4] : a[i]) + recv;
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = up ? a[i] : a[i + 2];
+      float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      a[i] = (up ? a[i + 2] : a[i]) + recv;
+    }
+  }
+  {
+    const bool up = lane & 1;
+    float send = up ? a[0] : a[1];
+    float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    a[0] = (up ? a[1] : a[0]) + recv;
+  }
+  if (NV < 32) a[0] += __shfl_xor_sync(0xffffffffu, a[0], 16);   // both half-warps hold 16 columns
+  return a[0];
+}
+// column index (within the NV-wide chunk) whose sum lane `lane` holds after warp_colsum
+template <int NV>
+__device__ __forceinline__ int warp_colsum_index(int lane) {
+  // lane bit 16 chose columns [16,32), bit 8 the upper 8 of those, ... : the index equals the lane
+  // bits themselves for NV == 32; for NV == 16 the low four bits.
+  return NV >= 32 ? (lane & 31) : (lane & 15);
+}
+template <int NV>
+__device__ __forceinline__ void warp_colsum_atomic(float* dst, int n0, int nvalid, const float* v) {
+  if constexpr (NV == 16 || NV == 32) {   // only the tensor-core epilogue (one row per lane) fuses column sums
+    const int lane = threadIdx.x & 31;
+    float s = warp_colsum<NV>(v, lane);
+    int c = warp_colsum_index<NV>(lane);
+    if (c < nvalid && (NV >= 32 || lane < 16) && s != 0.f) atomicAdd(dst + n0 + c, s);
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- out = act(acc + bias[n] + addend[m,n])  (+= when accumulate) -----------------------------
 // Forward MLP layers (base.py:46-60: relu(h W + b), last layer linear) and plain stores.
 template <typename OutT>
@@ -111,7 +186,8 @@ struct EpiStore {
   float scale;
 
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
+    if (!valid) return;
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = acc[i] * scale;
@@ -157,27 +233,44 @@ struct EpiBCE {
   float* nll_acc;           // scalar accumulator: += -inv_bg * sum(w * loglik)
   float inv_bg;             // 1 / global batch
   float partial;
+  float* colsum;            // fused bias gradient db[n] += sum_m dlogits[m,n] (tensor-core path only) or null
+  int fast;                 // 1: fast intrinsics (bf16 mode), 0: accurate libm (fp32 validation mode)
 
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
     float xv[NV], d[NV];
-    load_frag<NV>(x + (int64_t)(m / x_row_div) * ldx + n0, xv, nvalid);
-    float w = row_weight ? __ldg(row_weight + m) : 1.f;
+    if (valid) {
+      load_frag<NV>(x + (int64_t)(m / x_row_div) * ldx + n0, xv, nvalid);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = 0.f;
+    }
+    float w = (valid && row_weight) ? __ldg(row_weight + m) : 1.f;
     float ll = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float l = acc[i] + gen_bias;
       if (bias && i < nvalid) l += __ldg(bias + n0 + i);
-      float e = __expf(-fabsf(l));
-      float sp = fmaxf(l, 0.f) + log1pf(e);
-      float inv1pe = 1.f / (1.f + e);
+      float e, sp, inv1pe;
+      if (fast) {
+        e = __expf(-fabsf(l));
+        sp = fmaxf(l, 0.f) + __logf(1.f + e);
+        inv1pe = __frcp_rn(1.f + e);
+      } else {
+        e = expf(-fabsf(l));
+        sp = fmaxf(l, 0.f) + log1pf(e);
+        inv1pe = 1.f / (1.f + e);
+      }
       float sg = l >= 0.f ? inv1pe : e * inv1pe;
       if (i < nvalid) ll += xv[i] * l - sp;
-      d[i] = (sg - xv[i]) * (w * inv_bg);
+      d[i] = (valid && i < nvalid) ? (sg - xv[i]) * (w * inv_bg) : 0.f;
     }
-    store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
-    if (row_sum) atomicAdd(row_sum + m, ll);
-    partial += w * ll;
+    if (valid) {
+      store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
+      if (row_sum) atomicAdd(row_sum + m, ll);
+      partial += w * ll;
+    }
+    if (colsum) warp_colsum_atomic<NV>(colsum, n0, nvalid, d);
   }
   __device__ __forceinline__ void finish_warp() {
     float s = warp_sum(partial);
@@ -191,13 +284,25 @@ template <typename OutT, typename HT>
 struct EpiReluMask {
   OutT* out; int64_t ld;
   const HT* h; int64_t ldh;
+  float* colsum;            // fused bias gradient of the layer below (tensor-core path only) or null
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
     float hv[NV], v[NV];
-    load_frag<NV>(h + (int64_t)m * ldh + n0, hv, nvalid);
+    if (valid) {
+      load_frag<NV>(h + (int64_t)m * ldh + n0, hv, nvalid);
+    } else {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = hv[i] > 0.f ? acc[i] : 0.f;
-    store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
+      for (int i = 0; i < NV; ++i) hv[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = (hv[i] > 0.f && i < nvalid) ? acc[i] : 0.f;
+    if (valid) store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
+    if (colsum) {
+      // the bias gradient sums the values as stored (bf16-rounded when OutT is bf16)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = to_f32<OutT>(from_f32<OutT>(v[i]));
+      warp_colsum_atomic<NV>(colsum, n0, nvalid, v);
+    }
   }
   __device__ __forceinline__ void finish_warp() {}
 };
@@ -206,11 +311,17 @@ struct EpiReluMask {
 struct EpiAtomicAdd {
   float* out; int64_t ld;
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
+    if (!valid) return;
     float* dst = out + (int64_t)m * ld + n0;
+    if (NV % 4 == 0 && nvalid == NV && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i < nvalid) atomicAdd(dst + i, acc[i]);
+      for (int i = 0; i < NV; i += 4) red_add_v4(dst + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (i < nvalid) atomicAdd(dst + i, acc[i]);
+    }
   }
   __device__ __forceinline__ void finish_warp() {}
 };

@@ -17,6 +17,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gmvae {
@@ -36,6 +38,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -149,47 +154,58 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
-template <int BLOCK_N> __host__ __device__ constexpr int stages_for() { return BLOCK_N >= 256 ? 4 : 3; }
 template <int BLOCK_N> __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2; }
+// as many ring stages as fit in ~196 KB (one persistent CTA per SM), at most 8
+template <int BLOCK_N> __host__ __device__ constexpr int stages_for() {
+  return (196 * 1024) / stage_bytes<BLOCK_N>() > 8 ? 8 : (196 * 1024) / stage_bytes<BLOCK_N>();
+}
 template <int BLOCK_N> __host__ __device__ constexpr int smem_bytes() { return stages_for<BLOCK_N>() * stage_bytes<BLOCK_N>() + 1024 /*align*/ + 256 /*barriers*/; }
+
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant
+constexpr int NUM_THREADS2 = 64 + EPI_WARPS * 32;  // + TMA producer warp + MMA warp
 
 struct GemmMaps {
   CUtensorMap a1, b1, a2, b2;
 };
 
+// Persistent, warp-specialised: each CTA walks tiles t = blockIdx.x, +gridDim.x, ... of the
+// (n fastest, then m, then k-split) tile space.  The accumulator is double-buffered in TMEM so
+// the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS)
-gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int kb2, int kb_per_split, Epi epi_in) {
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int kb2, int kb_per_split, int num_splits, Epi epi_in) {
   constexpr int STAGES = stages_for<BLOCK_N>();
   constexpr int STAGE_BYTES = stage_bytes<BLOCK_N>();
-  constexpr int TMEM_COLS = tmem_cols_for(BLOCK_N);
+  constexpr int ACC_COLS = tmem_cols_for(BLOCK_N);         // column stride between the two accumulators
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int CW = (BLOCK_N % 32 == 0) ? 32 : 16;
+  constexpr int NCHUNK = BLOCK_N / CW;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
   static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B is loaded in 64-column slabs");
   static_assert((BLOCK_N * BLOCK_K * 2) % 1024 == 0, "stage buffers must stay 1024-byte aligned");
+  static_assert(TMEM_COLS <= 512, "two accumulators must fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int total_tiles = tiles_mn * num_splits;
   const int kb_total = kb1 + kb2;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(kb_total, kb_begin + kb_per_split);
-  const int nkb = kb_end - kb_begin;
-  if (nkb <= 0) return;  // uniform across the CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a1);
     tma_prefetch_desc(&maps.b1);
     if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -203,28 +219,33 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const bool seg2 = kb >= kb1;
-        const CUtensorMap* ta = seg2 ? &maps.a2 : &maps.a1;
-        const CUtensorMap* tb = seg2 ? &maps.b2 : &maps.b1;
-        const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        uint8_t* sb = sa + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-        if (A_MN) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int z = t / tiles_mn, mn = t - z * tiles_mn;
+        const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
+        const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool seg2 = kb >= kb1;
+          const CUtensorMap* ta = seg2 ? &maps.a2 : &maps.a1;
+          const CUtensorMap* tb = seg2 ? &maps.b2 : &maps.b1;
+          const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (A_MN) {
 #pragma unroll
-          for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
-        } else {
-          tma_load_2d(ta, &full_bar[stage], sa, k_elem, m0);
-        }
-        if (B_MN) {
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+          } else {
+            tma_load_2d(ta, &full_bar[stage], sa, k_elem, m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(tb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
-        } else {
-          tma_load_2d(tb, &full_bar[stage], sb, k_elem, n0);
+            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(tb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
+          } else {
+            tma_load_2d(tb, &full_bar[stage], sb, k_elem, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -232,38 +253,58 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
       // ===== MMA issuer (single thread) =====
       constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int z = t / tiles_mn;
+        const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+        const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], ap ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc<A_MN>(sa);
-        const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc<A_MN>(sa);
+          const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          umma_bf16(adesc + (uint64_t)(k * desc_k_step<A_MN>()), bdesc + (uint64_t)(k * desc_k_step<B_MN>()), tmem_base, idesc,
-                    (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(adesc + (uint64_t)(k * desc_k_step<A_MN>()), bdesc + (uint64_t)(k * desc_k_step<B_MN>()), tmem_d, idesc,
+                      (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[as]);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====
     Epi epi = epi_in;
-    const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int e = warp - 2;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = e >> 2;             // the two warps of a quadrant interleave column chunks
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int z = t / tiles_mn, mn = t - z * tiles_mn;
+      const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
+      const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+      const int m = m0 + quad * 32 + lane;
+      mbar_wait(&tmem_full_bar[as], ap);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += CW) {
-      float v[CW];
-      if constexpr (CW == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
-      const int n = n0 + c;
-      if (m < M && n < N) epi.template row<CW>(m, n, v, min(CW, N - n));
+      for (int ci = half; ci < NCHUNK; ci += 2) {
+        float v[CW];
+        if constexpr (CW == 32) tmem_ld32(taddr + ci * CW, v); else tmem_ld16(taddr + ci * CW, v);
+        const int n = n0 + ci * CW;
+        if (n < N) epi.template row<CW>(m, n, v, min(CW, N - n), m < M);   // warp-uniform call
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      epi.finish_warp();
     }
-    epi.finish_warp();
   }
   tc_fence_before();
   __syncthreads();
@@ -291,9 +332,11 @@ struct Operand {
   const bf16* ptr; int64_t ld; int rows; int k;
 };
 
+int num_sms();
+
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, const Operand* B2, int M, int N, int split_k,
-                   const Epi& epi, cudaStream_t st) {
+                   const Epi& epi, cudaStream_t st, bool persistent = true) {
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, Epi>;
   if (!attr_set) {
@@ -319,8 +362,9 @@ int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, cons
   if (split_k < 1) split_k = 1;
   int per = (kb_total + split_k - 1) / split_k;
   split_k = (kb_total + per - 1) / per;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M, split_k);
-  kern<<<grid, NUM_THREADS, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, epi);
+  const int total = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M) * split_k;
+  const int grid = persistent ? std::min(total, num_sms()) : total;
+  kern<<<grid, NUM_THREADS2, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, split_k, epi);
   GM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

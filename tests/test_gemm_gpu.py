@@ -39,7 +39,8 @@ def _bf16(t):
 # K-major x K-major: forward / dgrad shapes.  A [M,K], B stored [N,K].
 @pytest.mark.parametrize("M,N,K", [
     (128, 128, 64), (128, 64, 128), (100, 512, 784), (256, 784, 512), (300, 128, 512), (100, 64, 512),
-    (129, 1024, 64), (16384, 512, 512), (100, 112, 72), (1000, 256, 1024),
+    (129, 1024, 64), (16384, 512, 512), (100, 112, 72), (1000, 256, 1024), (16384, 784, 512), (4000, 10, 512),
+    (4000, 512, 10), (3000, 24, 40), (20000, 128, 10),
 ])
 def test_tc_gemm_kmajor(eng, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
@@ -52,7 +53,8 @@ def test_tc_gemm_kmajor(eng, M, N, K):
 # MN-major x MN-major: weight-gradient shapes.  A stored [K,M], B stored [K,N]; K = batch.
 @pytest.mark.parametrize("M,N,K,split", [
     (128, 128, 64, 1), (128, 64, 128, 1), (512, 512, 100, 1), (784, 512, 100, 2), (512, 784, 256, 3),
-    (64, 512, 1000, 4), (512, 128, 16384, 37), (200, 136, 333, 2),
+    (64, 512, 1000, 4), (512, 128, 16384, 37), (200, 136, 333, 2), (512, 512, 16384, 18), (784, 512, 16384, 10),
+    (10, 512, 5000, 8), (512, 10, 5000, 8),
 ])
 def test_tc_gemm_mnmajor(eng, M, N, K, split):
     g = torch.Generator().manual_seed(M + N + K)
