@@ -181,8 +181,8 @@ static void plan_buf(gmvae_handle* h, const std::string& name, size_t bytes) {
 
 static void plan_mlp_bufs(gmvae_handle* h, const Mlp& m, size_t B, size_t asz) {
   for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
-    plan_buf(h, m.name + ".h" + std::to_string(i), B * m.layers[i].out * asz);
-    plan_buf(h, m.name + ".dh" + std::to_string(i), B * m.layers[i].out * asz);
+    plan_buf(h, m.name + ".h" + std::to_string(i), B * round_up(m.layers[i].out, 8) * asz);
+    plan_buf(h, m.name + ".dh" + std::to_string(i), B * round_up(m.layers[i].out, 8) * asz);
   }
 }
 
@@ -219,13 +219,13 @@ static int plan(gmvae_handle* h) {
   // ---- workspace ----
   const size_t B = (size_t)c.max_batch, asz = h->act_size();
   const int Kp = round_up(K, 8);
-  plan_buf(h, "x_act", B * D * asz);
+  plan_buf(h, "x_act", B * round_up(D, 8) * asz);
   plan_buf(h, "eps", B * Z * 4);
-  plan_buf(h, "dec.dlogits", B * D * asz);
+  plan_buf(h, "dec.dlogits", B * round_up(D, 8) * asz);
   plan_buf(h, "dz", B * Z * 4);
   plan_buf(h, "enc_out", B * 2 * Z * 4);
-  plan_buf(h, "d_enc_out", B * 2 * Z * asz);
-  plan_buf(h, "z_act", B * Z * asz);
+  plan_buf(h, "d_enc_out", B * round_up(2 * Z, 8) * asz);
+  plan_buf(h, "z_act", B * round_up(Z, 8) * asz);
   plan_mlp_bufs(h, h->decoder, B, asz);
   plan_mlp_bufs(h, h->encoder, B, asz);
   if (c.model == GMVAE_MODEL_GMVAE) {
@@ -235,7 +235,7 @@ static int plan(gmvae_handle* h) {
     plan_buf(h, "y_f32", B * K * 4);
     plan_buf(h, "y_act", B * Kp * asz);
     plan_buf(h, "prior_out", B * 2 * Z * 4);
-    plan_buf(h, "d_prior_out", B * 2 * Z * asz);
+    plan_buf(h, "d_prior_out", B * round_up(2 * Z, 8) * asz);
     plan_buf(h, "dy", B * K * 4);
     plan_buf(h, "dlogits_y", B * Kp * asz);
     plan_buf(h, "pre_y", B * (size_t)(h->hidden.empty() ? 2 * Z : h->hidden[0]) * 4);
@@ -312,10 +312,10 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
 }
 
 // C[M,out] = A[M,in] * W (+ A2[M,in2] * W2)        forward through a linear layer
-template <typename TA, class Epi>
+template <typename TA, class Epi, bool ALLOW_TC = true>
 static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinView& L, const Epi& epi, cudaStream_t st,
                    const TA* A2 = nullptr, int64_t lda2 = 0, const LinView* L2 = nullptr) {
-  if constexpr (std::is_same<TA, bf16>::value) {
+  if constexpr (ALLOW_TC && std::is_same<TA, bf16>::value) {
     bool ok = tc_ok_fwd<TA>(h, A, lda, L);
     if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->wt_bf16);
     if (ok) {
@@ -392,6 +392,10 @@ static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, fl
 }
 
 // ============================================================================ MLP passes
+// Every GEMM-operand activation buffer has its row stride rounded up to 8 elements (16 bytes, the
+// TMA requirement); the padding columns are never written and stay zero from allocation.
+static inline int ldp(int n) { return round_up(n, 8); }
+
 template <typename A> struct MlpBufs { std::vector<A*> hid, dhid; };
 
 template <typename A>
@@ -404,16 +408,17 @@ static MlpBufs<A> mlp_bufs(const gmvae_handle* h, const Mlp& m) {
   return b;
 }
 
-// Hidden layers i >= first of an MLP: h[i] = relu(h[i-1] W_i + b_i). Layer 0's input is `in0`.
+// Hidden layers i >= first of an MLP: h[i] = relu(h[i-1] W_i + b_i). Layer 0's input is `in0`
+// (row stride ld0) and multiplies the first `in0_cols` rows of W_0.
 template <typename A>
-static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int M, int first,
-                          cudaStream_t st) {
+static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols, int M,
+                          int first, cudaStream_t st) {
   const int nh = (int)m.layers.size() - 1;
   for (int i = first; i < nh; ++i) {
     const A* in = i == 0 ? in0 : b.hid[i - 1];
-    int64_t ld = i == 0 ? ld0 : m.layers[i - 1].out;
-    LinView L = view(h, m.layers[i], 0, i == 0 ? (int)std::min<int64_t>(m.layers[0].in, ld0) : -1);
-    EpiStore<A> epi{b.hid[i], (int64_t)m.layers[i].out, L.b, nullptr, 0, 1, 0, 1.f};
+    int64_t ld = i == 0 ? ld0 : ldp(m.layers[i - 1].out);
+    LinView L = view(h, m.layers[i], 0, i == 0 ? in0_cols : -1);
+    EpiStore<A> epi{b.hid[i], (int64_t)ldp(m.layers[i].out), L.b, nullptr, 0, 1, 1.f};
     GM_TRY(lin_fwd<A>(h, in, ld, M, L, epi, st));
   }
   return 0;
@@ -423,26 +428,28 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
 // Computes every dW, db and the hidden gradients down to dh[0]; the gradient w.r.t. the MLP
 // input is left to the caller (it is only needed for z and y, never for the image x).
 // `in0_cols` = how many leading rows of W_0 multiply `in0` (encoder_gmm: D of D+K).
+// On the tensor-core path the dgrad epilogue that writes dh[i-1] also reduces its columns, which
+// is the bias gradient of layer i-1 (no separate pass over dh).
 template <typename A, typename TD>
 static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols,
                         const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false) {
   const int nl = (int)m.layers.size();
   const bool fuse = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
   bool bias_done = dout_bias_done;   // bias gradient of the layer whose output gradient we hold
-  // last layer
   {
     const Linear& l = m.layers[nl - 1];
     const bool first = nl == 1;
     LinView L = view(h, l, 0, first ? in0_cols : -1);
     const A* in = first ? in0 : b.hid[nl - 2];
-    int64_t ld = first ? ld0 : m.layers[nl - 2].out;
+    int64_t ld = first ? ld0 : ldp(m.layers[nl - 2].out);
     GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
     if (!bias_done) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
+    bias_done = false;
     if (!first) {
       LinView Lf = view(h, l);
-      // the tensor-core epilogue also reduces the columns of what it stores = bias gradient of layer nl-2
+      const int64_t ldh = ldp(m.layers[nl - 2].out);
       float* cs = (fuse && tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf)) ? h->grads + m.layers[nl - 2].b_off : nullptr;
-      EpiReluMask<A, A> epi{b.dhid[nl - 2], (int64_t)m.layers[nl - 2].out, b.hid[nl - 2], (int64_t)m.layers[nl - 2].out, cs};
+      EpiReluMask<A, A> epi{b.dhid[nl - 2], ldh, b.hid[nl - 2], ldh, cs};
       GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
       bias_done = cs != nullptr;
     }
@@ -452,15 +459,17 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
     const bool first = i == 0;
     LinView L = view(h, l, 0, first ? in0_cols : -1);
     const A* in = first ? in0 : b.hid[i - 1];
-    int64_t ld = first ? ld0 : m.layers[i - 1].out;
-    GM_TRY((lin_wgrad<A, A>(h, in, ld, b.dhid[i], l.out, M, L, st)));
-    if (!bias_done) GM_TRY(bias_grad<A>(h, b.dhid[i], l.out, M, l.out, L.db, st));
+    int64_t ld = first ? ld0 : ldp(m.layers[i - 1].out);
+    const int64_t ldd = ldp(l.out);
+    GM_TRY((lin_wgrad<A, A>(h, in, ld, b.dhid[i], ldd, M, L, st)));
+    if (!bias_done) GM_TRY(bias_grad<A>(h, b.dhid[i], ldd, M, l.out, L.db, st));
     bias_done = false;
     if (!first) {
       LinView Lf = view(h, l);
-      float* cs = (fuse && tc_ok_dgrad<A>(h, b.dhid[i], l.out, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
-      EpiReluMask<A, A> epi{b.dhid[i - 1], (int64_t)m.layers[i - 1].out, b.hid[i - 1], (int64_t)m.layers[i - 1].out, cs};
-      GM_TRY((lin_dgrad<A>(h, b.dhid[i], l.out, M, Lf, epi, st)));
+      const int64_t ldh = ldp(m.layers[i - 1].out);
+      float* cs = (fuse && tc_ok_dgrad<A>(h, b.dhid[i], ldd, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
+      EpiReluMask<A, A> epi{b.dhid[i - 1], ldh, b.hid[i - 1], ldh, cs};
+      GM_TRY((lin_dgrad<A>(h, b.dhid[i], ldd, M, Lf, epi, st)));
       bias_done = cs != nullptr;
     }
   }
@@ -473,6 +482,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
                                  const float* u_in, cudaStream_t st) {
   const gmvae_config& c = h->cfg;
   const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
+  const int Dp = ldp(D), Zp = ldp(Z), Z2p = ldp(2 * Z), Kp = ldp(K);
   const float inv_bg = 1.f / (float)Bg;
   const bool gm = c.model == GMVAE_MODEL_GMVAE;
   float* acc = h->grads + h->n_params;
@@ -481,8 +491,9 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
 
   A* x_act = h->buf<A>("x_act");
   {
-    int64_t n = (int64_t)B * D;
-    convert_x_kernel<A><<<(unsigned)((n / 16 + 255) / 256 + 1), 256, 0, st>>>(x_u8, x_act, n);
+    const int64_t n = (int64_t)B * D;
+    if (D % 16 == 0) convert_x_kernel<A><<<(unsigned)((n / 16 + 255) / 256), 256, 0, st>>>(x_u8, x_act, n);
+    else convert_x_rows_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_u8, x_act, B, D, Dp);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_MISC);
   }
   const float* eps = eps_in; const float* u = u_in;
@@ -502,64 +513,62 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   A* z_act = h->buf<A>("z_act");
   float* dz = h->buf<float>("dz");
   A* dlogits_x = h->buf<A>("dec.dlogits");
-  const int Kp = round_up(K, 8);
   const Linear& enc_l0 = h->encoder.layers[0];
   const Linear& enc_last = h->encoder.layers[nl - 1];
+  auto hid_ld = [&](int i) { return (int64_t)ldp(h->hidden[i]); };
 
   // -------------------------------------------------------------------------- forward
   MlpBufs<A> ey; float *logits_y = nullptr, *y_f32 = nullptr, *prior_out = nullptr; A* y_act = nullptr;
-  bool two_seg = false;
   if (gm) {
     ey = mlp_bufs<A>(h, h->encoder_y);
     logits_y = h->buf<float>("logits_y"); y_f32 = h->buf<float>("y_f32"); y_act = h->buf<A>("y_act");
     prior_out = h->buf<float>("prior_out");
     // q(y|x): encoder_y MLP, logits in fp32 (gmvae.py:238)
-    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, D, B, 0, st));
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, Dp, D, B, 0, st));
     {
       const Linear& l = h->encoder_y.layers[nl - 1];
-      EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 0, 1.f};
-      GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? D : h->hidden[nl - 2], B, view(h, l), epi, st));
+      EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
+      GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
     head_y_fwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, u, B, K, 1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
     // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
     {
       const Linear& l = h->prior_gmm.layers[0];
-      EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 0, 1.f};
+      EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 1.f};
       GM_TRY(lin_fwd<A>(h, y_act, Kp, B, view(h, l), epi, st));
     }
     // q(z|x,y) layer 0: [x,y] W = x W[:D] + y W[D:]  (no concat, base.py:66)
     LinView Lx = view(h, enc_l0, 0, D), Ly = view(h, enc_l0, D, K);
     const bool last0 = nl == 1;
-    two_seg = std::is_same<A, bf16>::value && h->bf16_mode() && !(h->debug_flags & (DBG_NO_TC | DBG_NO_TWO_SEG)) && D % 8 == 0 &&
-              D >= 32 && enc_l0.out >= 32;
+    const bool two_seg = tc_ok_fwd<A>(h, x_act, Dp, Lx) && tc_ok_fwd<A>(h, y_act, Kp, Ly) && !(h->debug_flags & DBG_NO_TWO_SEG);
     if (two_seg) {
       if (last0) {
-        EpiStore<float> epi{enc_out, (int64_t)2 * Z, Lx.b, nullptr, 0, 0, 0, 1.f};
-        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st, y_act, Kp, &Ly));
+        EpiStore<float> epi{enc_out, (int64_t)2 * Z, Lx.b, nullptr, 0, 0, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
       } else {
-        EpiStore<A> epi{enc.hid[0], (int64_t)enc_l0.out, Lx.b, nullptr, 0, 1, 0, 1.f};
-        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st, y_act, Kp, &Ly));
+        EpiStore<A> epi{enc.hid[0], hid_ld(0), Lx.b, nullptr, 0, 1, 1.f};
+        GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
       }
-    } else {
+    } else {   // fp32 validation mode: pre = y W[D:] + b, then relu(x W[:D] + pre)   (CUDA-core GEMMs)
       float* pre = h->buf<float>("pre_y");
-      EpiStore<float> e0{pre, (int64_t)enc_l0.out, Lx.b, nullptr, 0, 0, 0, 1.f};
-      GM_TRY(lin_fwd<A>(h, y_act, Kp, B, Ly, e0, st));
+      EpiStore<float> e0{pre, (int64_t)enc_l0.out, Lx.b, nullptr, 0, 0, 1.f};
+      GM_TRY((lin_fwd<A, EpiStore<float>, false>(h, y_act, Kp, B, Ly, e0, st)));
       if (last0) {
-        EpiStore<float> epi{enc_out, (int64_t)2 * Z, nullptr, pre, (int64_t)enc_l0.out, 0, 0, 1.f};
-        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st));
+        EpiStore<float, EPI_ADDEND> epi{enc_out, (int64_t)2 * Z, nullptr, pre, (int64_t)enc_l0.out, 0, 1.f};
+        GM_TRY((lin_fwd<A, EpiStore<float, EPI_ADDEND>, false>(h, x_act, Dp, B, Lx, epi, st)));
       } else {
-        EpiStore<A> epi{enc.hid[0], (int64_t)enc_l0.out, nullptr, pre, (int64_t)enc_l0.out, 1, 0, 1.f};
-        GM_TRY(lin_fwd<A>(h, x_act, D, B, Lx, epi, st));
+        EpiStore<A, EPI_ADDEND> epi{enc.hid[0], hid_ld(0), nullptr, pre, (int64_t)enc_l0.out, 1, 1.f};
+        GM_TRY((lin_fwd<A, EpiStore<A, EPI_ADDEND>, false>(h, x_act, Dp, B, Lx, epi, st)));
       }
     }
-    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, D, B, 1, st));
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, B, 1, st));
   } else {
-    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, D, B, 0, st));
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, B, 0, st));
   }
   if (nl > 1 || !gm) {   // last encoder layer -> enc_out (fp32)
-    EpiStore<float> epi{enc_out, (int64_t)2 * Z, h->params + enc_last.b_off, nullptr, 0, 0, 0, 1.f};
-    GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : enc.hid[nl - 2], nl == 1 ? D : h->hidden[nl - 2], B, view(h, enc_last, 0, nl == 1 ? D : -1),
+    EpiStore<float> epi{enc_out, (int64_t)2 * Z, h->params + enc_last.b_off, nullptr, 0, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : enc.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, enc_last, 0, nl == 1 ? D : -1),
                       epi, st));
   }
   // z head
@@ -568,7 +577,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   {
     int64_t n = (int64_t)B * Z;
     head_z_fwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, prior_mode, B, Z, c.raw_sigma_bias,
-                                                                    c.sigma_min, inv_bg, z_act, z_f32, acc);
+                                                                    c.sigma_min, inv_bg, z_act, Zp, z_f32, acc);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
   float* dz_prior = h->buf<float>("dz_prior");
@@ -579,61 +588,59 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
         h->grads + h->loc_off, h->grads + h->raw_scale_off, h->grads + h->mix_off, acc);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
+  // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood (and db of that layer)
   bool dec_bias_fused = false;
-  // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood
-  GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Z, B, 0, st));
+  GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Zp, Z, B, 0, st));
   {
     const Linear& l = h->decoder.layers[nl - 1];
     const A* in = nl == 1 ? z_act : dec.hid[nl - 2];
-    const int64_t ldin = nl == 1 ? Z : h->hidden[nl - 2];
+    const int64_t ldin = nl == 1 ? Zp : hid_ld(nl - 2);
     LinView Ld = view(h, l);
     dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, in, ldin, Ld);
-    EpiBCE<A> epi{dlogits_x, (int64_t)D, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, nullptr,
+    EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, nullptr,
                   acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
     GM_TRY(lin_fwd<A>(h, in, ldin, B, Ld, epi, st));
   }
 
   // -------------------------------------------------------------------------- backward
-  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Z, Z, dlogits_x, D, B, st, dec_bias_fused)));
+  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, B, st, dec_bias_fused)));
   {  // dz = d(first decoder layer input)
     const Linear& l0 = h->decoder.layers[0];
-    EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 0, 1.f};
-    if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, D, B, view(h, l0), epi, st)));
-    else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], l0.out, B, view(h, l0), epi, st)));
+    EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 1.f};
+    if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, Dp, B, view(h, l0), epi, st)));
+    else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], hid_ld(0), B, view(h, l0), epi, st)));
   }
   A* d_prior_out = h->buf<A>("d_prior_out");
   {
     int64_t n = (int64_t)B * Z;
     head_z_bwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, dz, dz_prior, prior_mode, B, Z,
-                                                                    c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, d_prior_out);
+                                                                    c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, d_prior_out, Z2p);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
   }
-  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, D, D, d_enc_out, 2 * Z, B, st)));
+  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st)));
   if (gm) {
     float* dy = h->buf<float>("dy"); A* dlogits_y = h->buf<A>("dlogits_y");
     LinView Ly = view(h, enc_l0, D, K);
     // y-columns of encoder_gmm layer 0: dW[D:] = y^T dh0 ; dy = dh0 W[D:]^T
-    if (nl == 1) {
-      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_enc_out, 2 * Z, B, Ly, st)));
-      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
-      GM_TRY((lin_dgrad<A>(h, d_enc_out, 2 * Z, B, Ly, e, st)));
-    } else {
-      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, enc.dhid[0], enc_l0.out, B, Ly, st)));
-      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 0, 1.f};
-      GM_TRY((lin_dgrad<A>(h, enc.dhid[0], enc_l0.out, B, Ly, e, st)));
+    const A* dh0 = nl == 1 ? d_enc_out : enc.dhid[0];
+    const int64_t ld_dh0 = nl == 1 ? Z2p : hid_ld(0);
+    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, dh0, ld_dh0, B, Ly, st)));
+    {
+      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
+      GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st)));
     }
     // prior_gmm: dWp = y^T d_prior_out ; dbp ; dy += d_prior_out Wp^T
     {
       const Linear& l = h->prior_gmm.layers[0];
       LinView Lp = view(h, l);
-      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, 2 * Z, B, Lp, st)));
-      GM_TRY(bias_grad<A>(h, d_prior_out, 2 * Z, B, 2 * Z, Lp.db, st));
-      EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1, 1.f};
-      GM_TRY((lin_dgrad<A>(h, d_prior_out, 2 * Z, B, Lp, e, st)));
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
+      GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
+      EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
+      GM_TRY((lin_dgrad<A>(h, d_prior_out, Z2p, B, Lp, e, st)));
     }
     head_y_bwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
-    GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, D, D, dlogits_y, Kp, B, st)));
+    GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st)));
   }
   return 0;
 }
@@ -905,9 +912,12 @@ int gmvae_profile_read(gmvae_handle* h, double* ms_by_class, int64_t* launches_b
 }
 
 // ---- kernel-level test hook ------------------------------------------------------------------
-__global__ void dbg_to_bf16(const float* in, bf16* out, int64_t n) {
+__global__ void dbg_to_bf16(const float* in, bf16* out, int64_t rows, int64_t cols, int64_t ld) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+  if (i < rows * ld) {
+    int64_t r = i / ld, c = i % ld;
+    out[i] = __float2bfloat16_rn(c < cols ? in[r * cols + c] : 0.f);
+  }
 }
 
 int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K, const float* A, const float* B,
@@ -921,22 +931,24 @@ int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, i
     GM_CHECK_CUDA((launch_gemm_simt<float, float, EpiAtomicAdd>(A, sAm, sAk, B, sBk, sBn, M, N, K, split_k, epi, st)));
     return 0;
   }
-  // tcgen05 path: operands converted to bf16 scratch (allocated here; test hook only).
+  // tcgen05 path: operands converted to bf16 scratch, rows padded to 16 bytes (test hook only).
   // A stored [M,K] (transA=0 -> K-major) or [K,M] (transA=1 -> MN-major);
   // B stored [K,N] (transB=0 -> MN-major) or [N,K] (transB=1 -> K-major).
   const bool a_mn = transA != 0, b_mn = transB == 0;
   GM_REQUIRE(a_mn == b_mn, "debug hook covers K-major x K-major and MN-major x MN-major");
+  const int64_t a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+  const int64_t lda = round_up((int)a_cols, 8), ldb = round_up((int)b_cols, 8);
   bf16 *a16 = nullptr, *b16 = nullptr;
-  GM_CHECK_CUDA(cudaMalloc(&a16, (size_t)M * K * 2));
-  GM_CHECK_CUDA(cudaMalloc(&b16, (size_t)N * K * 2));
-  dbg_to_bf16<<<(unsigned)(((int64_t)M * K + 255) / 256), 256, 0, st>>>(A, a16, (int64_t)M * K);
-  dbg_to_bf16<<<(unsigned)(((int64_t)N * K + 255) / 256), 256, 0, st>>>(B, b16, (int64_t)N * K);
+  GM_CHECK_CUDA(cudaMalloc(&a16, (size_t)a_rows * lda * 2));
+  GM_CHECK_CUDA(cudaMalloc(&b16, (size_t)b_rows * ldb * 2));
+  dbg_to_bf16<<<(unsigned)((a_rows * lda + 255) / 256), 256, 0, st>>>(A, a16, a_rows, a_cols, lda);
+  dbg_to_bf16<<<(unsigned)((b_rows * ldb + 255) / 256), 256, 0, st>>>(B, b16, b_rows, b_cols, ldb);
   int r;
   if (!a_mn) {
-    tc::Operand a{a16, K, M, K}, b{b16, K, N, K};
+    tc::Operand a{a16, lda, M, kpad(K, lda)}, b{b16, ldb, N, kpad(K, ldb)};
     r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, epi, st);
   } else {
-    tc::Operand a{a16, M, M, K}, b{b16, N, N, K};
+    tc::Operand a{a16, lda, kpad(M, lda), K}, b{b16, ldb, kpad(N, ldb), K};
     r = N <= 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
         : N <= 128 ? tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st)
                    : tc::launch_gemm_tc<256, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, M, N, split_k, epi, st);

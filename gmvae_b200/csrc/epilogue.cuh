@@ -173,47 +173,55 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// ---- out = act(acc + bias[n] + addend[m,n])  (+= when accumulate) -----------------------------
+// Every functor has a two-phase interface so that a kernel can issue the epilogue's own global
+// loads (bias, ReLU mask, image bytes) BEFORE it waits for the accumulator:
+//     auto pre = epi.template prefetch<NV>(m, n0, nvalid, valid);
+//     ... wait for acc ...
+//     epi.template row<NV>(m, n0, acc, nvalid, valid, pre);
+// `valid` is false for rows beyond M; such lanes must still take part in warp-wide reductions.
+
+// ---- out = act(acc + bias[n] (+ addend[m,n]))  (out += ... when ACCUM) -------------------------
 // Forward MLP layers (base.py:46-60: relu(h W + b), last layer linear) and plain stores.
-template <typename OutT>
+enum { EPI_PLAIN = 0, EPI_ADDEND = 1, EPI_ACCUM = 2 };
+template <typename OutT, int MODE = EPI_PLAIN>
 struct EpiStore {
   OutT* out; int64_t ld;
   const float* bias;        // [N] or null
-  const float* addend;      // [M, ld_add] fp32 or null (the y-part of encoder_gmm layer 0 in fp32 mode)
+  const float* addend;      // EPI_ADDEND: [M, ld_add] fp32 (the y-part of encoder_gmm layer 0 in fp32 mode)
   int64_t ld_add;
   int relu;
-  int accumulate;           // out += value (fp32 outputs only; rows are owned by one thread)
   float scale;
 
+  template <int NV> struct Pre { float b[NV]; float a[(MODE != EPI_PLAIN) ? NV : 1]; };
+
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+    Pre<NV> p;
+    if (bias) {
+      load_frag<NV>(bias + n0, p.b, nvalid);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
+    }
+    if constexpr (MODE == EPI_ADDEND) {
+      if (valid) load_frag<NV>(addend + (int64_t)m * ld_add + n0, p.a, nvalid);
+    } else if constexpr (MODE == EPI_ACCUM) {
+      if (valid) load_frag<NV>(out + (int64_t)m * ld + n0, p.a, nvalid);
+    }
+    return p;
+  }
+  template <int NV>
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
     if (!valid) return;
     float v[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = acc[i] * scale;
-    if (bias) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (i < nvalid) v[i] += __ldg(bias + n0 + i);
+    for (int i = 0; i < NV; ++i) {
+      v[i] = fmaf(acc[i], scale, p.b[i]);
+      if constexpr (MODE == EPI_ADDEND) v[i] += p.a[i];
+      if (relu) v[i] = fmaxf(v[i], 0.f);
+      if constexpr (MODE == EPI_ACCUM) v[i] += p.a[i];
     }
-    if (addend) {
-      float a[NV];
-      load_frag<NV>(addend + (int64_t)m * ld_add + n0, a, nvalid);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] += a[i];
-    }
-    if (relu) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
-    OutT* dst = out + (int64_t)m * ld + n0;
-    if (accumulate) {
-      float o[NV];
-      load_frag<NV>(dst, o, nvalid);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] += o[i];
-    }
-    store_frag<NV>(dst, v, nvalid);
+    store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
   }
   __device__ __forceinline__ void finish_warp() {}
 };
@@ -236,41 +244,61 @@ struct EpiBCE {
   float* colsum;            // fused bias gradient db[n] += sum_m dlogits[m,n] (tensor-core path only) or null
   int fast;                 // 1: fast intrinsics (bf16 mode), 0: accurate libm (fp32 validation mode)
 
+  template <int NV> struct Pre { float b[NV]; float x[NV]; float w; };
+
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
-    float xv[NV], d[NV];
-    if (valid) {
-      load_frag<NV>(x + (int64_t)(m / x_row_div) * ldx + n0, xv, nvalid);
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+    Pre<NV> p;
+    if (bias) {
+      load_frag<NV>(bias + n0, p.b, nvalid);
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) xv[i] = 0.f;
+      for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
     }
-    float w = (valid && row_weight) ? __ldg(row_weight + m) : 1.f;
+    if (valid) {
+      load_frag<NV>(x + (int64_t)(m / x_row_div) * ldx + n0, p.x, nvalid);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) p.x[i] = 0.f;
+    }
+    p.w = (valid && row_weight) ? __ldg(row_weight + m) : 1.f;
+    return p;
+  }
+  template <int NV>
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
+    float d[NV];
     float ll = 0.f;
+    const float wscale = p.w * inv_bg;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float l = acc[i] + gen_bias;
-      if (bias && i < nvalid) l += __ldg(bias + n0 + i);
+      const float l = acc[i] + gen_bias + p.b[i];
       float e, sp, inv1pe;
       if (fast) {
+        // exp(-|l|) in (0,1]; log(1+e) with 1+e in (1,2]: absolute error of the intrinsics ~1e-7
         e = __expf(-fabsf(l));
         sp = fmaxf(l, 0.f) + __logf(1.f + e);
-        inv1pe = __frcp_rn(1.f + e);
+        inv1pe = __fdividef(1.f, 1.f + e);
       } else {
         e = expf(-fabsf(l));
         sp = fmaxf(l, 0.f) + log1pf(e);
         inv1pe = 1.f / (1.f + e);
       }
-      float sg = l >= 0.f ? inv1pe : e * inv1pe;
-      if (i < nvalid) ll += xv[i] * l - sp;
-      d[i] = (valid && i < nvalid) ? (sg - xv[i]) * (w * inv_bg) : 0.f;
+      const float sg = l >= 0.f ? inv1pe : e * inv1pe;
+      const bool ok = valid && i < nvalid;
+      ll += ok ? fmaf(p.x[i], l, -sp) : 0.f;
+      d[i] = ok ? (sg - p.x[i]) * wscale : 0.f;
     }
     if (valid) {
       store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
       if (row_sum) atomicAdd(row_sum + m, ll);
-      partial += w * ll;
+      partial += p.w * ll;
     }
-    if (colsum) warp_colsum_atomic<NV>(colsum, n0, nvalid, d);
+    if (colsum) {
+      // the bias gradient sums the values as stored (bf16-rounded when OutT is bf16)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) d[i] = to_f32<OutT>(from_f32<OutT>(d[i]));
+      warp_colsum_atomic<NV>(colsum, n0, nvalid, d);
+    }
   }
   __device__ __forceinline__ void finish_warp() {
     float s = warp_sum(partial);
@@ -285,17 +313,25 @@ struct EpiReluMask {
   OutT* out; int64_t ld;
   const HT* h; int64_t ldh;
   float* colsum;            // fused bias gradient of the layer below (tensor-core path only) or null
+
+  template <int NV> struct Pre { float h[NV]; };
+
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
-    float hv[NV], v[NV];
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+    Pre<NV> p;
     if (valid) {
-      load_frag<NV>(h + (int64_t)m * ldh + n0, hv, nvalid);
+      load_frag<NV>(h + (int64_t)m * ldh + n0, p.h, nvalid);
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) hv[i] = 0.f;
+      for (int i = 0; i < NV; ++i) p.h[i] = 0.f;
     }
+    return p;
+  }
+  template <int NV>
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
+    float v[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = (hv[i] > 0.f && i < nvalid) ? acc[i] : 0.f;
+    for (int i = 0; i < NV; ++i) v[i] = (p.h[i] > 0.f && i < nvalid) ? acc[i] : 0.f;
     if (valid) store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
     if (colsum) {
       // the bias gradient sums the values as stored (bf16-rounded when OutT is bf16)
@@ -307,11 +343,14 @@ struct EpiReluMask {
   __device__ __forceinline__ void finish_warp() {}
 };
 
-// ---- split-K weight gradient: out[m,n] += acc (fp32 atomics into the flat gradient buffer) ----
+// ---- split-K weight gradient: out[m,n] += acc (fp32 reductions into the flat gradient buffer) ----
 struct EpiAtomicAdd {
   float* out; int64_t ld;
+  template <int NV> struct Pre {};
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid = true) {
+  __device__ __forceinline__ Pre<NV> prefetch(int, int, int, bool) const { return Pre<NV>(); }
+  template <int NV>
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>&) {
     if (!valid) return;
     float* dst = out + (int64_t)m * ld + n0;
     if (NV % 4 == 0 && nvalid == NV && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {

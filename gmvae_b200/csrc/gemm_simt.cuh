@@ -64,7 +64,11 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sAm, int64_t sAk, const TB* _
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int m = m0 + ty * 4 + i;
-      if (m < M && n < N) epi.template row<4>(m, n, acc[i], min(4, N - n));
+      if (m < M && n < N) {
+        const int nv = min(4, N - n);
+        auto pre = epi.template prefetch<4>(m, n, nv, true);
+        epi.template row<4>(m, n, acc[i], nv, true, pre);
+      }
     }
   }
   epi.finish_warp();

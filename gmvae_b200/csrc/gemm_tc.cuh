@@ -98,22 +98,24 @@ __device__ __forceinline__ void umma_bf16(uint64_t adesc, uint64_t bdesc, uint32
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// tcgen05.ld is asynchronous: the destination registers are valid only after tcgen05.wait::ld.
+// The wait takes the registers as in/out operands so the compiler cannot move a use above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -123,9 +125,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // ---- descriptors ---------------------------------------------------------------------------
@@ -295,10 +303,17 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
 #pragma unroll 1
       for (int ci = half; ci < NCHUNK; ci += 2) {
-        float v[CW];
-        if constexpr (CW == 32) tmem_ld32(taddr + ci * CW, v); else tmem_ld16(taddr + ci * CW, v);
         const int n = n0 + ci * CW;
-        if (n < N) epi.template row<CW>(m, n, v, min(CW, N - n), m < M);   // warp-uniform call
+        if (n >= N) break;                               // warp-uniform
+        const int nv = min(CW, N - n);
+        uint32_t r[CW];
+        if constexpr (CW == 32) tmem_ld32_issue(taddr + ci * CW, r); else tmem_ld16_issue(taddr + ci * CW, r);
+        auto pre = epi.template prefetch<CW>(m, n, nv, m < M);   // global loads fly while TMEM is read
+        if constexpr (CW == 32) tmem_ld32_wait(r); else tmem_ld16_wait(r);
+        float v[CW];
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+        epi.template row<CW>(m, n, v, nv, m < M, pre);
       }
       tc_fence_before();
       __syncwarp();

@@ -34,6 +34,16 @@ __global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ 
   }
 }
 
+// generic variant: rows of D bytes -> rows of ld elements (ld >= D; padding left untouched)
+template <typename T>
+__global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int B, int D, int ld) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)B * D) {
+    int64_t r = i / D, c = i % D;
+    out[r * ld + c] = from_f32<T>((float)x[i]);
+  }
+}
+
 // ---- noise (only when the caller does not inject it) -----------------------------------------
 // eps ~ N(0,1) (tf.random_normal inside MultivariateNormalDiag.sample), u ~ U(tiny,1)
 // (RelaxedOneHotCategorical.sample).  Keyed by (seed, step, stream id, element index).
@@ -171,7 +181,7 @@ __global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float*
 template <typename ActT>
 __global__ void head_z_fwd_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
                                   const float* __restrict__ prior_out, int prior_mode, int B, int Z, float c,
-                                  float sigma_min, float inv_bg, ActT* __restrict__ z_act, float* __restrict__ z_f32,
+                                  float sigma_min, float inv_bg, ActT* __restrict__ z_act, int ld_z, float* __restrict__ z_f32,
                                   float* __restrict__ acc) {
   __shared__ float scratch[32];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +192,7 @@ __global__ void head_z_fwd_kernel(const float* __restrict__ enc_out, const float
     float sg = fmaxf(softplus_f(raw + c), sigma_min);
     float e = eps[i];
     float z = fmaf(sg, e, mu);
-    z_act[i] = from_f32<ActT>(z);
+    z_act[(int64_t)b * ld_z + j] = from_f32<ActT>(z);
     if (z_f32) z_f32[i] = z;
     float logq = -0.5f * e * e - logf(sg);
     float logp = 0.f;
@@ -208,7 +218,7 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
                                   const float* __restrict__ prior_out, const float* __restrict__ dz_dec,
                                   const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c,
                                   float sigma_min, float inv_bg, ActT* __restrict__ d_enc_out,
-                                  ActT* __restrict__ d_prior_out) {
+                                  ActT* __restrict__ d_prior_out, int ld_out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Z) return;
   int b = (int)(i / Z), j = (int)(i % Z);
@@ -230,12 +240,12 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
     float isp2 = 1.f / (sp * sp);
     dz += d * isp2 * inv_bg;
     float dsp = (1.f / sp - d * d * isp2 / sp) * inv_bg;
-    d_prior_out[(int64_t)b * 2 * Z + j] = from_f32<ActT>(-d * isp2 * inv_bg);
-    d_prior_out[(int64_t)b * 2 * Z + Z + j] = from_f32<ActT>(spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f);
+    d_prior_out[(int64_t)b * ld_out + j] = from_f32<ActT>(-d * isp2 * inv_bg);
+    d_prior_out[(int64_t)b * ld_out + Z + j] = from_f32<ActT>(spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f);
   }
   float dsg = dz * e - inv_bg / sg;
-  d_enc_out[(int64_t)b * 2 * Z + j] = from_f32<ActT>(dz);
-  d_enc_out[(int64_t)b * 2 * Z + Z + j] = from_f32<ActT>(spq >= sigma_min ? dsg * sigmoid_f(raw + c) : 0.f);
+  d_enc_out[(int64_t)b * ld_out + j] = from_f32<ActT>(dz);
+  d_enc_out[(int64_t)b * ld_out + Z + j] = from_f32<ActT>(spq >= sigma_min ? dsg * sigmoid_f(raw + c) : 0.f);
 }
 
 // ---- VAE_GMP mixture prior (vae.py:231-244, 181): forward value and every gradient -------------

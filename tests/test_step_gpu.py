@@ -98,7 +98,7 @@ def test_adam_first_step_known_answer():
     eng.adam_step()
     lr1 = 3.1622776601683816e-4
     want = p0.double() - lr1 * 0.1 * g.double() / ((0.001 * g.double() ** 2).sqrt() + 1e-8)
-    assert (eng.params.double() - want).abs().max().item() < 1e-9
+    assert (eng.params.double() - want).abs().max().item() < 1e-7   # fp32 arithmetic on |theta| ~ 0.3
     assert eng.global_step == 1
     eng.close()
 
