@@ -25,6 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ["NCCL_DEBUG"] = os.environ.get("GMVAE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+
 import torch  # noqa: E402
 
 WORKLOADS = {
@@ -96,7 +98,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -192,7 +194,7 @@ def run_gpu_arm(args, w):
     B = args.batch or w["batch"]
     eng = gmvae_b200.Engine(model=w["model"], data_size=D, latent_size=w["latent_size"], hidden_sizes=w["hidden_sizes"],
                             mixture_components=w["mixture_components"], precision=args.precision, objective=args.objective,
-                            max_batch=B, device=local, seed=1234 + rank)
+                            max_batch=B, device=local, seed=1234)   # same weights on every rank; noise is keyed by rank
     if world > 1:
         eng.init_data_parallel()
 

@@ -136,8 +136,14 @@ struct gmvae_handle {
   // per-launch CUDA-event profile (off by default; bench.py turns it on for a few eager steps)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, int>> marks;
-  // NCCL
+  // NCCL: gradients are all-reduced in buckets ordered by backward readiness, on a side stream
   ncclComm_t comm = nullptr; int world = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int comm_ev_next = 0;
+  bool overlap_comm = false;             // set by gmvae_train_step
+  int64_t reduced_upto = 0;              // floats of `grads` already handed to NCCL this step
+  int64_t bucket_end[2] = {0, 0};        // flat offsets where bucket 0 (decoder) / 1 (encoder, prior) end
   // graph
   cudaGraphExec_t graph_exec = nullptr;
 
@@ -201,19 +207,25 @@ static int plan(gmvae_handle* h) {
   h->L = c.num_hidden + 1;
   const int D = h->D, Z = h->Z, K = h->K;
   auto with = [&](int last) { std::vector<int> v = h->hidden; v.push_back(last); return v; };
-  // Variable order = graph-construction order of the reference factories.
-  if (c.model == GMVAE_MODEL_GMVAE) {                       // gmvae.py:321-353
-    build_mlp(h, h->prior_gmm, "prior_gmm", K, std::vector<int>{2 * Z});
+  // The variables are the reference's (gmvae.py:321-353, vae.py:231-268), laid out in the flat
+  // buffer in the order their gradients become final during the backward pass, so that the
+  // data-parallel all-reduce can start on the decoder's range while the encoders are still running.
+  if (c.model == GMVAE_MODEL_GMVAE) {
     build_mlp(h, h->decoder, "decoder", Z, with(D));
-    build_mlp(h, h->encoder_y, "encoder_y", D, with(K));
+    h->bucket_end[0] = h->n_params;
     build_mlp(h, h->encoder, "encoder_gmm", D + K, with(2 * Z));
-  } else {                                                  // vae.py:231-268
+    build_mlp(h, h->prior_gmm, "prior_gmm", K, std::vector<int>{2 * Z});
+    h->bucket_end[1] = h->n_params;
+    build_mlp(h, h->encoder_y, "encoder_y", D, with(K));
+  } else {
+    build_mlp(h, h->decoder, "decoder", Z, with(D));
+    h->bucket_end[0] = h->n_params;
     if (c.model == GMVAE_MODEL_VAE_GMP) {
       add_param(h, "loc", K, Z, &h->loc_off);
       add_param(h, "raw_scale_diag", K, Z, &h->raw_scale_off);
       add_param(h, "mixture_logits", 1, K, &h->mix_off);
     }
-    build_mlp(h, h->decoder, "decoder", Z, with(D));
+    h->bucket_end[1] = h->n_params;                         // nothing else is final before the end
     build_mlp(h, h->encoder, "encoder", D, with(2 * Z));
   }
   // ---- workspace ----
@@ -271,6 +283,22 @@ static int profile_mark(gmvae_handle* h, cudaStream_t st, int cls) {
   GM_CHECK_CUDA(cudaEventCreate(&e));
   GM_CHECK_CUDA(cudaEventRecord(e, st));
   h->marks.emplace_back(e, cls);
+  return 0;
+}
+
+// Hands grads[reduced_upto, upto) to NCCL on the side stream once everything enqueued on `st` so
+// far (which produced that range) has finished.  No-op outside gmvae_train_step / without a
+// communicator.  All ranks issue the same sequence of collectives.
+static int comm_bucket(gmvae_handle* h, cudaStream_t st, int64_t upto) {
+  if (!h->comm || h->world == 1 || !h->overlap_comm || upto <= h->reduced_upto) return 0;
+  cudaEvent_t ev = h->comm_ev[h->comm_ev_next++ % 8];
+  GM_CHECK_CUDA(cudaEventRecord(ev, st));
+  GM_CHECK_CUDA(cudaStreamWaitEvent(h->comm_stream, ev, 0));
+  ncclResult_t r = ncclAllReduce(h->grads + h->reduced_upto, h->grads + h->reduced_upto, (size_t)(upto - h->reduced_upto), ncclFloat,
+                                 ncclSum, h->comm, h->comm_stream);
+  if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return -5; }
+  h->reduced_upto = upto;
+  h->launches++;
   return 0;
 }
 
@@ -488,6 +516,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   float* acc = h->grads + h->n_params;
   if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
   GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  h->reduced_upto = 0;
 
   A* x_act = h->buf<A>("x_act");
   {
@@ -610,6 +639,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, Dp, B, view(h, l0), epi, st)));
     else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], hid_ld(0), B, view(h, l0), epi, st)));
   }
+  GM_TRY(comm_bucket(h, st, h->bucket_end[0]));     // decoder gradients are final
   A* d_prior_out = h->buf<A>("d_prior_out");
   {
     int64_t n = (int64_t)B * Z;
@@ -638,6 +668,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, d_prior_out, Z2p, B, Lp, e, st)));
     }
+    GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     head_y_bwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp);
     GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
     GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st)));
@@ -709,6 +740,8 @@ void gmvae_destroy(gmvae_handle* h) {
   if (!h) return;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->comm) ncclCommDestroy(h->comm);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  for (auto& e : h->comm_ev) if (e) cudaEventDestroy(e);
   if (h->shadow_dev) cudaFree(h->shadow_dev);
   if (h->state) cudaFree(h->state);
   delete h;
@@ -830,12 +863,25 @@ int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int ran
   ncclResult_t r = ncclCommInitRank(&h->comm, world_size, uid, rank);
   if (r != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); return -5; }
   h->world = world_size; h->rank = rank;
+  GM_CHECK_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  for (auto& e : h->comm_ev) GM_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
 int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
   GM_TRY(check_ready(h));
   if (!h->comm || h->world == 1) return 0;
-  ncclResult_t r = ncclAllReduce(h->grads, h->grads, (size_t)(h->n_params + ACC_SLOTS), ncclFloat, ncclSum, h->comm, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = h->n_params + ACC_SLOTS;
+  if (h->overlap_comm) {
+    // the buckets issued during the backward pass cover [0, reduced_upto); finish the rest on the
+    // side stream and join it back into the caller's stream
+    GM_TRY(comm_bucket(h, st, total));
+    cudaEvent_t ev = h->comm_ev[h->comm_ev_next++ % 8];
+    GM_CHECK_CUDA(cudaEventRecord(ev, h->comm_stream));
+    GM_CHECK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    return 0;
+  }
+  ncclResult_t r = ncclAllReduce(h->grads, h->grads, (size_t)total, ncclFloat, ncclSum, h->comm, st);
   if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return -5; }
   h->launches++;
   return 0;
@@ -843,8 +889,11 @@ int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
 
 int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps, const float* gumbel_u,
                      float* loss_terms, void* stream) {
-  GM_TRY(gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream));
-  GM_TRY(gmvae_allreduce_grads(h, stream));
+  h->overlap_comm = h->comm != nullptr && h->world > 1;
+  int r = gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream);
+  if (r == 0) r = gmvae_allreduce_grads(h, stream);
+  h->overlap_comm = false;
+  GM_TRY(r);
   if (loss_terms) GM_TRY(gmvae_finalize_loss(h, loss_terms, stream));
   return gmvae_adam_step(h, stream);
 }
