@@ -106,7 +106,8 @@ struct Philox {
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
   }
 };
-// uniform in (0,1): never 0, never 1
-__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1): never 0, never 1.  (r>>9)+0.5 is exact in fp32 (23 bits + half), so the
+// largest value is 1 - 2^-24 and the smallest 2^-24.
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 }  // namespace gmvae

@@ -937,6 +937,17 @@ int gmvae_prior_table(gmvae_handle*, float*, float*, void*) {
   return -6;
 }
 
+int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int64_t n_u, void* stream) {
+  GM_REQUIRE(h, "null argument");
+  if (!eps) n_eps = 0;
+  if (!u) n_u = 0;
+  int64_t q = (n_eps + 3) / 4 + (n_u + 3) / 4;
+  if (q == 0) return 0;
+  fill_noise_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eps, n_eps, u, n_u, h->state, (uint64_t)h->rank);
+  GM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int gmvae_profile_enable(gmvae_handle* h, int on) {
   GM_REQUIRE(h, "null argument");
   for (auto& m : h->marks) cudaEventDestroy(m.first);

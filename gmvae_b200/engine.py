@@ -272,6 +272,14 @@ class Engine:
         self.lib.gmvae_profile_read(self._h, ms, n, 8)
         return {name: {"ms": ms[i], "launches": int(n[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
 
+    def debug_noise(self, n_eps: int, n_u: int):
+        """Draws from the step's device noise generator (test hook)."""
+        e = torch.empty(n_eps, dtype=torch.float32, device=self.device)
+        u = torch.empty(n_u, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.gmvae_debug_noise(self._h, e.data_ptr() if n_eps else None, n_eps, u.data_ptr() if n_u else None,
+                                              n_u, self._stream()), "gmvae_debug_noise")
+        return e, u
+
     def debug_gemm(self, impl: int, A: torch.Tensor, B: torch.Tensor, transA=False, transB=False, split_k=1) -> torch.Tensor:
         """C = op(A) op(B) through the step's own GEMM kernels (impl 0 SIMT fp32, 1 tcgen05 bf16)."""
         A = A.to(self.device, torch.float32).contiguous(); B = B.to(self.device, torch.float32).contiguous()

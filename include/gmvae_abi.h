@@ -155,6 +155,10 @@ GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* 
 GMVAE_API int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K,
                      const float* A, const float* B, float* C, int split_k, void* stream);
 
+/* Test hook: the step's own noise generator (Philox4x32-10) writing n_eps N(0,1) draws and n_u
+ * uniforms in the OPEN interval (0,1) into caller buffers (either may be NULL / 0). */
+GMVAE_API int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int64_t n_u, void* stream);
+
 /* Per-launch profile: with profiling on, a CUDA event is recorded after every launch of the
  * (eager) step; read() returns the summed device time and launch count per kernel class:
  * 0 tcgen05 GEMM fwd/dgrad, 1 tcgen05 GEMM wgrad, 2 SIMT GEMM, 3 distribution heads,

@@ -141,6 +141,19 @@ def test_device_noise_statistics():
     eng.close()
 
 
+def test_device_noise_generator_range_and_moments():
+    """u must lie in the OPEN interval (0,1) (u = 1 would give a Gumbel of +inf and NaN), eps ~ N(0,1)."""
+    eng = make_engine(CONFIGS["tiny_vae"], "bf16"); eng.initialize(1)
+    e, u = eng.debug_noise(1 << 26, 1 << 28)       # 2.7e8 uniforms: the 2^-24 endpoint would show ~16 times
+    assert 0.0 < u.min().item() and u.max().item() < 1.0
+    assert abs(u.mean().item() - 0.5) < 1e-3
+    assert abs(e.mean().item()) < 1e-3 and abs(e.std().item() - 1.0) < 1e-3
+    assert torch.isfinite(e).all()
+    k = (e.double() ** 4).mean().item()
+    assert abs(k - 3.0) < 0.02                     # Gaussian kurtosis
+    eng.close()
+
+
 def test_dropin_classes_run_model():
     import gmvae_b200
     spec = make_spec(CONFIGS["cfg3"])
