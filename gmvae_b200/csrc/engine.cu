@@ -43,6 +43,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+long long* g_trace = nullptr;
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1004,6 +1006,33 @@ int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, i
   dbg_to_bf16<<<(unsigned)((a_rows * lda + 255) / 256), 256, 0, st>>>(A, a16, a_rows, a_cols, lda);
   dbg_to_bf16<<<(unsigned)((b_rows * ldb + 255) / 256), 256, 0, st>>>(B, b16, b_rows, b_cols, ldb);
   int r;
+  if (impl >= 2) {
+    // traced run of a forward-style layer: out = relu(A B^T + bias) in bf16; the first 4096 int64 of C
+    // receive CTA 0's clock64 stamps (16 per tile: see gemm_tc.cuh)
+    GM_REQUIRE(!a_mn && (size_t)M * N * 4 >= 4096 * 8, "trace needs K-major operands and a large enough C");
+    bf16* o16 = nullptr; float* bias = nullptr; long long* tr = nullptr;
+    GM_CHECK_CUDA(cudaMalloc(&o16, (size_t)M * round_up(N, 8) * 2));
+    GM_CHECK_CUDA(cudaMalloc(&bias, (size_t)N * 4));
+    GM_CHECK_CUDA(cudaMalloc(&tr, 4096 * 8));
+    GM_CHECK_CUDA(cudaMemsetAsync(bias, 0, (size_t)N * 4, st));
+    GM_CHECK_CUDA(cudaMemsetAsync(tr, 0, 4096 * 8, st));
+    tc::Operand a{a16, lda, M, kpad(K, lda)}, b{b16, ldb, N, kpad(K, ldb)};
+    tc::g_trace = tr;
+    if (impl == 2) {
+      EpiStore<bf16> e2{o16, (int64_t)round_up(N, 8), bias, nullptr, 0, 1, 1.f};
+      r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, e2, st);
+    } else {
+      EpiReluMask<bf16, bf16> e3{o16, (int64_t)round_up(N, 8), a16, lda, impl == 4 ? bias : nullptr};
+      r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, e3, st);
+    }
+    tc::g_trace = nullptr;
+    GM_CHECK_CUDA(cudaMemcpyAsync(C, tr, 4096 * 8, cudaMemcpyDeviceToDevice, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(o16); cudaFree(bias); cudaFree(tr); cudaFree(a16); cudaFree(b16);
+    if (r != 0) return r;
+    GM_CHECK_CUDA(e);
+    return 0;
+  }
   if (!a_mn) {
     tc::Operand a{a16, lda, M, kpad(K, lda)}, b{b16, ldb, N, kpad(K, ldb)};
     r = tc_dispatch_kk(h, a, b, nullptr, nullptr, M, N, epi, st);

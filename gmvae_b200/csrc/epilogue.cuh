@@ -7,6 +7,8 @@
 // gradient (gmvae.py:254 / vae.py:177), ReLU masks of the backward pass, atomic accumulation of
 // split-K weight gradients.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gmvae {
@@ -173,12 +175,143 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---- coalesced epilogue I/O for the tensor-core kernel ---------------------------------------
+// In the tcgen05 epilogue lane l of a warp owns row (m_base + l) of a 32-row x NV-column chunk.
+// Storing that row by row makes every store instruction touch 32 different cache lines with a
+// 16-byte piece each (measured: ~2300 cycles per chunk).  Instead the warp transposes the chunk
+// through a private 2 KB shared-memory patch (XOR-swizzled, conflict-free both ways) so that one
+// global instruction covers 8 rows x 64 contiguous bytes (NV = 32) or 16 rows x 32 bytes (NV = 16).
+struct EpiCtx {
+  uint8_t* patch;   // per-warp scratch (>= 2 KB) or null (CUDA-core GEMM: rows are stored directly)
+  int rows_valid;   // valid rows of the warp's 32-row group (lane l <-> row m_base + l)
+  const float* sbias;  // tensor-core kernel: this chunk's bias values staged in shared memory by tile_begin()
+};
+// Chunks are moved in 16-byte pieces; a ragged last chunk (N not a multiple of NV) rounds its
+// width up to 8 columns, which stays inside the zero padding of the row (strides are multiples of 8).
+__device__ __forceinline__ int cols8(int nvalid) { return (nvalid + 7) & ~7; }
+template <int NV> __device__ __forceinline__ int swz(int r) { return NV == 32 ? ((r >> 1) & 3) : 0; }
+
+// all 32 lanes call; lane l passes its row's NV values.  rows_valid = number of valid rows of the chunk.
+// v[i] must be 0 for i >= nvalid (the rounded-up columns land in the row padding, which stays zero).
+template <int NV>
+__device__ __forceinline__ void store_chunk_bf16(bf16* base /*row m_base, col n0*/, int64_t ld, const float* v, int nvalid,
+                                                 const EpiCtx& ctx, bool keep_patch = false) {
+  constexpr int U = NV / 8;                         // 16-byte units per row
+  const int lane = threadIdx.x & 31;
+  const int rows_valid = ctx.rows_valid, ncols = cols8(nvalid);
+  const bool fast = (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+  uint4* patch = reinterpret_cast<uint4*>(ctx.patch);
+  if (!fast) {                                      // unaligned view: plain per-row store (patch still filled if kept)
+    if (lane < rows_valid) store_frag<NV>(base + (int64_t)lane * ld, v, nvalid);
+    if (!keep_patch) return;
+  }
+#pragma unroll
+  for (int c = 0; c < U; ++c) {
+    uint4 p;
+    p.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); p.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    p.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); p.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    patch[lane * U + (c ^ swz<NV>(lane))] = p;
+  }
+  __syncwarp();
+  constexpr int ROWS_PER_IT = 32 / U;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int r = ROWS_PER_IT * j + lane / U, c = lane % U;
+    const uint4 val = patch[r * U + (c ^ swz<NV>(r))];
+    if (fast && r < rows_valid && 8 * c < ncols) *reinterpret_cast<uint4*>(base + (int64_t)r * ld + 8 * c) = val;
+  }
+  if (!keep_patch) __syncwarp();
+}
+
+// Column sums of the chunk just staged in the patch by store_chunk_bf16 (call with keep_patch = true
+// there, then this, which ends with the releasing __syncwarp): lanes 0..15 / 16..31 each walk 16 rows
+// of a 32-bit column pair, one shuffle merges the halves, NV/2 lanes issue two atomics each.
+template <int NV>
+__device__ __forceinline__ void colsum_from_patch(float* dst, int n0, int nvalid, const EpiCtx& ctx) {
+  constexpr int U = NV / 8, WORDS = NV / 2;              // 32-bit words (column pairs) per row
+  const int lane = threadIdx.x & 31;
+  const uint32_t* patch = reinterpret_cast<const uint32_t*>(ctx.patch);
+  constexpr int LANES_PER_HALF = WORDS;                   // 16 (NV=32) or 8 (NV=16)
+  constexpr int GROUPS = 32 / LANES_PER_HALF;              // 2 or 4 row groups
+  constexpr int ROWS_PER_GROUP = 32 / GROUPS;
+  const int w = lane % LANES_PER_HALF, grp = lane / LANES_PER_HALF;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_GROUP; ++i) {
+    const int r = grp * ROWS_PER_GROUP + i;
+    const int c = w / 4;                                   // 16-byte unit holding this word
+    const uint32_t t = patch[(r * U + (c ^ swz<NV>(r))) * 4 + (w & 3)];
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t));
+    s0 += f.x; s1 += f.y;
+  }
+#pragma unroll
+  for (int o = LANES_PER_HALF; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (grp == 0) {
+    if (2 * w < nvalid && s0 != 0.f) atomicAdd(dst + n0 + 2 * w, s0);
+    if (2 * w + 1 < nvalid && s1 != 0.f) atomicAdd(dst + n0 + 2 * w + 1, s1);
+  }
+  __syncwarp();
+}
+
+// Coalesced load of a 32-row x NV-column bf16 chunk: phase 1 (issue) returns the raw 16-byte
+// pieces this lane fetched; phase 2 exchanges them through the patch and returns the lane's own row.
+template <int NV> struct ChunkRegs { uint4 q[NV / 8]; };
+template <int NV>
+__device__ __forceinline__ ChunkRegs<NV> load_chunk_bf16_issue(const bf16* base, int64_t ld, int nvalid, const EpiCtx& ctx) {
+  constexpr int U = NV / 8, ROWS_PER_IT = 32 / U;
+  const int lane = threadIdx.x & 31;
+  const int ncols = cols8(nvalid);
+  ChunkRegs<NV> g;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int r = ROWS_PER_IT * j + lane / U, c = lane % U;
+    g.q[j] = (r < ctx.rows_valid && 8 * c < ncols) ? *reinterpret_cast<const uint4*>(base + (int64_t)r * ld + 8 * c)
+                                                   : make_uint4(0, 0, 0, 0);
+  }
+  return g;
+}
+template <int NV>
+__device__ __forceinline__ void load_chunk_bf16_finish(const ChunkRegs<NV>& g, float* v, const EpiCtx& ctx) {
+  constexpr int U = NV / 8, ROWS_PER_IT = 32 / U;
+  const int lane = threadIdx.x & 31;
+  uint4* patch = reinterpret_cast<uint4*>(ctx.patch);
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int r = ROWS_PER_IT * j + lane / U, c = lane % U;
+    patch[r * U + (c ^ swz<NV>(r))] = g.q[j];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < U; ++c) {
+    const uint4 t = patch[lane * U + (c ^ swz<NV>(lane))];
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(p[k]);
+      v[8 * c + 2 * k] = f.x; v[8 * c + 2 * k + 1] = f.y;
+    }
+  }
+  __syncwarp();
+}
+
 // Every functor has a two-phase interface so that a kernel can issue the epilogue's own global
 // loads (bias, ReLU mask, image bytes) BEFORE it waits for the accumulator:
-//     auto pre = epi.template prefetch<NV>(m, n0, nvalid, valid);
+//     auto pre = epi.template prefetch<NV>(m, n0, nvalid, valid, ctx);
 //     ... wait for acc ...
-//     epi.template row<NV>(m, n0, acc, nvalid, valid, pre);
-// `valid` is false for rows beyond M; such lanes must still take part in warp-wide reductions.
+//     epi.template row<NV>(m, n0, acc, nvalid, valid, pre, ctx);
+// `valid` is false for rows beyond M.  With ctx.patch != null (tensor-core kernel) both calls are
+// warp-collective: all 32 lanes call them with consecutive rows m = m_base + lane.
+// tile_begin(n0, N, sbias, t, nt): called by the nt epilogue threads (t = 0..nt-1) of the tensor-core
+// kernel before they wait for a tile's accumulator; stages the tile's bias values in shared memory.
+template <int BN>
+__device__ __forceinline__ void stage_bias(const float* bias, int n0, int N, float* sbias, int t, int nt) {
+  for (int i = t; i < BN; i += nt) sbias[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+}
+
+template <typename T, int NV> struct staged_io { static constexpr bool value = std::is_same<T, bf16>::value && (NV == 16 || NV == 32); };
 
 // ---- out = act(acc + bias[n] (+ addend[m,n]))  (out += ... when ACCUM) -------------------------
 // Forward MLP layers (base.py:46-60: relu(h W + b), last layer linear) and plain stores.
@@ -192,16 +325,21 @@ struct EpiStore {
   int relu;
   float scale;
 
-  template <int NV> struct Pre { float b[NV]; float a[(MODE != EPI_PLAIN) ? NV : 1]; };
+  template <int NV> struct Pre { float b[NV >= 16 ? 1 : NV]; float a[(MODE != EPI_PLAIN) ? NV : 1]; };
+
+  template <int BN>
+  __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
 
   template <int NV>
-  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
     Pre<NV> p;
-    if (bias) {
-      load_frag<NV>(bias + n0, p.b, nvalid);
-    } else {
+    if constexpr (NV < 16) {
+      if (bias) {
+        load_frag<NV>(bias + n0, p.b, nvalid);
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
+        for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
+      }
     }
     if constexpr (MODE == EPI_ADDEND) {
       if (valid) load_frag<NV>(addend + (int64_t)m * ld_add + n0, p.a, nvalid);
@@ -211,15 +349,24 @@ struct EpiStore {
     return p;
   }
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
-    if (!valid) return;
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p, const EpiCtx& ctx) {
+    constexpr bool STAGED = staged_io<OutT, NV>::value && MODE == EPI_PLAIN;
+    if (!STAGED && !valid) return;
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      v[i] = fmaf(acc[i], scale, p.b[i]);
+      if constexpr (NV >= 16) v[i] = fmaf(acc[i], scale, ctx.sbias[i]); else v[i] = fmaf(acc[i], scale, p.b[i]);
       if constexpr (MODE == EPI_ADDEND) v[i] += p.a[i];
       if (relu) v[i] = fmaxf(v[i], 0.f);
       if constexpr (MODE == EPI_ACCUM) v[i] += p.a[i];
+      if (STAGED && i >= nvalid) v[i] = 0.f;
+    }
+    if constexpr (STAGED) {
+      if (ctx.patch) {
+        store_chunk_bf16<NV>(reinterpret_cast<bf16*>(out) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, v, nvalid, ctx);
+        return;
+      }
+      if (!valid) return;
     }
     store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
   }
@@ -244,16 +391,21 @@ struct EpiBCE {
   float* colsum;            // fused bias gradient db[n] += sum_m dlogits[m,n] (tensor-core path only) or null
   int fast;                 // 1: fast intrinsics (bf16 mode), 0: accurate libm (fp32 validation mode)
 
-  template <int NV> struct Pre { float b[NV]; float x[NV]; float w; };
+  template <int NV> struct Pre { float b[NV >= 16 ? 1 : NV]; float x[NV]; float w; };
+
+  template <int BN>
+  __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
 
   template <int NV>
-  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
     Pre<NV> p;
-    if (bias) {
-      load_frag<NV>(bias + n0, p.b, nvalid);
-    } else {
+    if constexpr (NV < 16) {
+      if (bias) {
+        load_frag<NV>(bias + n0, p.b, nvalid);
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
+        for (int i = 0; i < NV; ++i) p.b[i] = 0.f;
+      }
     }
     if (valid) {
       load_frag<NV>(x + (int64_t)(m / x_row_div) * ldx + n0, p.x, nvalid);
@@ -265,13 +417,14 @@ struct EpiBCE {
     return p;
   }
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p, const EpiCtx& ctx) {
     float d[NV];
     float ll = 0.f;
     const float wscale = p.w * inv_bg;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float l = acc[i] + gen_bias + p.b[i];
+      float l;
+      if constexpr (NV >= 16) l = acc[i] + gen_bias + ctx.sbias[i]; else l = acc[i] + gen_bias + p.b[i];
       float e, sp, inv1pe;
       if (fast) {
         // exp(-|l|) in (0,1]; log(1+e) with 1+e in (1,2]: absolute error of the intrinsics ~1e-7
@@ -289,15 +442,17 @@ struct EpiBCE {
       d[i] = ok ? (sg - p.x[i]) * wscale : 0.f;
     }
     if (valid) {
-      store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
       if (row_sum) atomicAdd(row_sum + m, ll);
       partial += p.w * ll;
     }
-    if (colsum) {
-      // the bias gradient sums the values as stored (bf16-rounded when OutT is bf16)
-#pragma unroll
-      for (int i = 0; i < NV; ++i) d[i] = to_f32<OutT>(from_f32<OutT>(d[i]));
-      warp_colsum_atomic<NV>(colsum, n0, nvalid, d);
+    if constexpr (staged_io<OutT, NV>::value) {
+      // tensor-core kernel: coalesced store through the warp's patch; the bias gradient (column sums
+      // of the values as stored, bf16-rounded) is read back from the same patch
+      store_chunk_bf16<NV>(reinterpret_cast<bf16*>(dlogits) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, d, nvalid, ctx,
+                           colsum != nullptr);
+      if (colsum) colsum_from_patch<NV>(colsum, n0, nvalid, ctx);
+    } else {
+      if (valid) store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
     }
   }
   __device__ __forceinline__ void finish_warp() {
@@ -314,30 +469,48 @@ struct EpiReluMask {
   const HT* h; int64_t ldh;
   float* colsum;            // fused bias gradient of the layer below (tensor-core path only) or null
 
-  template <int NV> struct Pre { float h[NV]; };
+  template <int NV> struct Pre {
+    float h[staged_io<HT, NV>::value ? 1 : NV];
+    ChunkRegs<staged_io<HT, NV>::value ? NV : 8> g;
+  };
+
+  template <int BN>
+  __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
 
   template <int NV>
-  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid) const {
+  __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx& ctx) const {
     Pre<NV> p;
-    if (valid) {
-      load_frag<NV>(h + (int64_t)m * ldh + n0, p.h, nvalid);
+    if constexpr (staged_io<HT, NV>::value) {
+      // coalesced: 16-byte pieces of the 32 x NV mask chunk, exchanged through the patch in row()
+      p.g = load_chunk_bf16_issue<NV>(reinterpret_cast<const bf16*>(h) + (int64_t)(m - (int)(threadIdx.x & 31)) * ldh + n0, ldh, nvalid, ctx);
     } else {
+      if (valid) {
+        load_frag<NV>(h + (int64_t)m * ldh + n0, p.h, nvalid);
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) p.h[i] = 0.f;
+        for (int i = 0; i < NV; ++i) p.h[i] = 0.f;
+      }
     }
     return p;
   }
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>& p, const EpiCtx& ctx) {
     float v[NV];
+    if constexpr (staged_io<HT, NV>::value) {
+      float hv[NV];
+      load_chunk_bf16_finish<NV>(p.g, hv, ctx);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = (p.h[i] > 0.f && i < nvalid) ? acc[i] : 0.f;
-    if (valid) store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
-    if (colsum) {
-      // the bias gradient sums the values as stored (bf16-rounded when OutT is bf16)
+      for (int i = 0; i < NV; ++i) v[i] = (hv[i] > 0.f && i < nvalid && valid) ? acc[i] : 0.f;
+    } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = to_f32<OutT>(from_f32<OutT>(v[i]));
-      warp_colsum_atomic<NV>(colsum, n0, nvalid, v);
+      for (int i = 0; i < NV; ++i) v[i] = (p.h[i] > 0.f && i < nvalid) ? acc[i] : 0.f;
+    }
+    if constexpr (staged_io<OutT, NV>::value) {
+      store_chunk_bf16<NV>(reinterpret_cast<bf16*>(out) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, v, nvalid, ctx,
+                           colsum != nullptr);
+      if (colsum) colsum_from_patch<NV>(colsum, n0, nvalid, ctx);   // bias gradient of the layer below, as stored
+    } else {
+      if (valid) store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
     }
   }
   __device__ __forceinline__ void finish_warp() {}
@@ -347,10 +520,12 @@ struct EpiReluMask {
 struct EpiAtomicAdd {
   float* out; int64_t ld;
   template <int NV> struct Pre {};
+  template <int BN>
+  __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
   template <int NV>
-  __device__ __forceinline__ Pre<NV> prefetch(int, int, int, bool) const { return Pre<NV>(); }
+  __device__ __forceinline__ Pre<NV> prefetch(int, int, int, bool, const EpiCtx&) const { return Pre<NV>(); }
   template <int NV>
-  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>&) {
+  __device__ __forceinline__ void row(int m, int n0, const float* acc, int nvalid, bool valid, const Pre<NV>&, const EpiCtx&) {
     if (!valid) return;
     float* dst = out + (int64_t)m * ld + n0;
     if (NV % 4 == 0 && nvalid == NV && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {

@@ -10,6 +10,7 @@
 // Transposes are expressed through the strides.  gridDim.z splits K (epilogue must be atomic).
 #pragma once
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace gmvae {
 
@@ -66,8 +67,9 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sAm, int64_t sAk, const TB* _
       int m = m0 + ty * 4 + i;
       if (m < M && n < N) {
         const int nv = min(4, N - n);
-        auto pre = epi.template prefetch<4>(m, n, nv, true);
-        epi.template row<4>(m, n, acc[i], nv, true, pre);
+        const EpiCtx ctx{nullptr, 0, nullptr};
+        auto pre = epi.template prefetch<4>(m, n, nv, true, ctx);
+        epi.template row<4>(m, n, acc[i], nv, true, pre, ctx);
       }
     }
   }

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace gmvae {
 namespace tc {
@@ -167,9 +168,13 @@ template <int BLOCK_N> __host__ __device__ constexpr int stage_bytes() { return 
 template <int BLOCK_N> __host__ __device__ constexpr int stages_for() {
   return (196 * 1024) / stage_bytes<BLOCK_N>() > 8 ? 8 : (196 * 1024) / stage_bytes<BLOCK_N>();
 }
-template <int BLOCK_N> __host__ __device__ constexpr int smem_bytes() { return stages_for<BLOCK_N>() * stage_bytes<BLOCK_N>() + 1024 /*align*/ + 256 /*barriers*/; }
-
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant
+constexpr int PATCH_BYTES = 2048;                  // per-epilogue-warp transposition scratch (epilogue.cuh)
+template <int BLOCK_N> __host__ __device__ constexpr int smem_bytes() {
+  return stages_for<BLOCK_N>() * stage_bytes<BLOCK_N>() + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * PATCH_BYTES +
+         2 * 256 * 4 /*double-buffered bias*/;
+}
+
 constexpr int NUM_THREADS2 = 64 + EPI_WARPS * 32;  // + TMA producer warp + MMA warp
 
 struct GemmMaps {
@@ -181,7 +186,7 @@ struct GemmMaps {
 // the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
-gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int kb2, int kb_per_split, int num_splits, Epi epi_in) {
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int kb2, int kb_per_split, int num_splits, long long* trace, Epi epi_in) {
   constexpr int STAGES = stages_for<BLOCK_N>();
   constexpr int STAGE_BYTES = stage_bytes<BLOCK_N>();
   constexpr int ACC_COLS = tmem_cols_for(BLOCK_N);         // column stride between the two accumulators
@@ -201,6 +206,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
   uint64_t* tmem_full_bar = bars + 2 * STAGES;        // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* patches = smem + STAGES * STAGE_BYTES + 256;
+  float* sbias_all = reinterpret_cast<float*>(patches + EPI_WARPS * PATCH_BYTES);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
@@ -227,10 +234,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int z = t / tiles_mn, mn = t - z * tiles_mn;
         const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
         const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+        if (trace && blockIdx.x == 0) trace[16 * it + 0] = clock64();
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const bool seg2 = kb >= kb1;
@@ -254,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (trace && blockIdx.x == 0) trace[16 * it + 1] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -266,12 +276,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
         const int z = t / tiles_mn;
         const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
         const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+        if (trace && blockIdx.x == 0) trace[16 * it + 2] = clock64();
         mbar_wait(&tmem_empty_bar[as], ap ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
+        if (trace && blockIdx.x == 0) trace[16 * it + 3] = clock64();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (trace && blockIdx.x == 0 && kb == kb_begin) trace[16 * it + 4] = clock64();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_smem_desc<A_MN>(sa);
           const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
@@ -284,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[as]);   // accumulator complete
+        if (trace && blockIdx.x == 0) trace[16 * it + 5] = clock64();
       }
     }
   } else {
@@ -298,8 +312,16 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
       const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
       const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
       const int m = m0 + quad * 32 + lane;
+      // stage this tile's bias while the MMA is still running; double-buffered, one named barrier per tile
+      float* sbias = sbias_all + (it & 1) * 256;
+      epi.template tile_begin<BLOCK_N>(n0, N, sbias, (int)threadIdx.x - 64, EPI_WARPS * 32);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      EpiCtx ctx{patches + e * PATCH_BYTES, max(0, min(32, M - (m0 + quad * 32))), sbias};
+      const bool tr = trace && blockIdx.x == 0 && e == 0 && lane == 0;
+      if (tr) trace[16 * it + 6] = clock64();
       mbar_wait(&tmem_full_bar[as], ap);
       tc_fence_after();
+      if (tr) trace[16 * it + 7] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
 #pragma unroll 1
       for (int ci = half; ci < NCHUNK; ci += 2) {
@@ -307,18 +329,21 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
         if (n >= N) break;                               // warp-uniform
         const int nv = min(CW, N - n);
         uint32_t r[CW];
+        ctx.sbias = sbias + ci * CW;
         if constexpr (CW == 32) tmem_ld32_issue(taddr + ci * CW, r); else tmem_ld16_issue(taddr + ci * CW, r);
-        auto pre = epi.template prefetch<CW>(m, n, nv, m < M);   // global loads fly while TMEM is read
+        auto pre = epi.template prefetch<CW>(m, n, nv, m < M, ctx);   // global loads fly while TMEM is read
         if constexpr (CW == 32) tmem_ld32_wait(r); else tmem_ld16_wait(r);
         float v[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
-        epi.template row<CW>(m, n, v, nv, m < M, pre);
+        epi.template row<CW>(m, n, v, nv, m < M, pre, ctx);
+        if (tr && ci / 2 < 4) trace[16 * it + 8 + ci / 2] = clock64();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
       epi.finish_warp();
+      if (tr) trace[16 * it + 12] = clock64();
     }
   }
   tc_fence_before();
@@ -348,6 +373,7 @@ struct Operand {
 };
 
 int num_sms();
+extern long long* g_trace;   // device buffer of clock64 stamps of CTA 0 (test hook), normally null
 
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, const Operand* B2, int M, int N, int split_k,
@@ -379,7 +405,7 @@ int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, cons
   split_k = (kb_total + per - 1) / per;
   const int total = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M) * split_k;
   const int grid = persistent ? std::min(total, num_sms()) : total;
-  kern<<<grid, NUM_THREADS2, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, split_k, epi);
+  kern<<<grid, NUM_THREADS2, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, split_k, g_trace, epi);
   GM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
