@@ -181,6 +181,29 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 // 16-byte piece each (measured: ~2300 cycles per chunk).  Instead the warp transposes the chunk
 // through a private 2 KB shared-memory patch (XOR-swizzled, conflict-free both ways) so that one
 // global instruction covers 8 rows x 64 contiguous bytes (NV = 32) or 16 rows x 32 bytes (NV = 16).
+// Explicit shared-space accesses: through a generic pointer the compiler emits LD.E/ST.E (generic
+// loads tracked on the long scoreboard) instead of LDS/STS.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
 struct EpiCtx {
   uint8_t* patch;   // per-warp scratch (>= 2 KB) or null (CUDA-core GEMM: rows are stored directly)
   int rows_valid;   // valid rows of the warp's 32-row group (lane l <-> row m_base + l)
@@ -200,7 +223,7 @@ __device__ __forceinline__ void store_chunk_bf16(bf16* base /*row m_base, col n0
   const int lane = threadIdx.x & 31;
   const int rows_valid = ctx.rows_valid, ncols = cols8(nvalid);
   const bool fast = (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
-  uint4* patch = reinterpret_cast<uint4*>(ctx.patch);
+  const uint32_t patch = smem_addr(ctx.patch);
   if (!fast) {                                      // unaligned view: plain per-row store (patch still filled if kept)
     if (lane < rows_valid) store_frag<NV>(base + (int64_t)lane * ld, v, nvalid);
     if (!keep_patch) return;
@@ -210,14 +233,14 @@ __device__ __forceinline__ void store_chunk_bf16(bf16* base /*row m_base, col n0
     uint4 p;
     p.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]); p.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
     p.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); p.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-    patch[lane * U + (c ^ swz<NV>(lane))] = p;
+    sts128(patch + 16 * (lane * U + (c ^ swz<NV>(lane))), p);
   }
   __syncwarp();
   constexpr int ROWS_PER_IT = 32 / U;
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int r = ROWS_PER_IT * j + lane / U, c = lane % U;
-    const uint4 val = patch[r * U + (c ^ swz<NV>(r))];
+    const uint4 val = lds128(patch + 16 * (r * U + (c ^ swz<NV>(r))));
     if (fast && r < rows_valid && 8 * c < ncols) *reinterpret_cast<uint4*>(base + (int64_t)r * ld + 8 * c) = val;
   }
   if (!keep_patch) __syncwarp();
@@ -230,7 +253,7 @@ template <int NV>
 __device__ __forceinline__ void colsum_from_patch(float* dst, int n0, int nvalid, const EpiCtx& ctx) {
   constexpr int U = NV / 8, WORDS = NV / 2;              // 32-bit words (column pairs) per row
   const int lane = threadIdx.x & 31;
-  const uint32_t* patch = reinterpret_cast<const uint32_t*>(ctx.patch);
+  const uint32_t patch = smem_addr(ctx.patch);
   constexpr int LANES_PER_HALF = WORDS;                   // 16 (NV=32) or 8 (NV=16)
   constexpr int GROUPS = 32 / LANES_PER_HALF;              // 2 or 4 row groups
   constexpr int ROWS_PER_GROUP = 32 / GROUPS;
@@ -240,7 +263,7 @@ __device__ __forceinline__ void colsum_from_patch(float* dst, int n0, int nvalid
   for (int i = 0; i < ROWS_PER_GROUP; ++i) {
     const int r = grp * ROWS_PER_GROUP + i;
     const int c = w / 4;                                   // 16-byte unit holding this word
-    const uint32_t t = patch[(r * U + (c ^ swz<NV>(r))) * 4 + (w & 3)];
+    const uint32_t t = lds32(patch + 4 * ((r * U + (c ^ swz<NV>(r))) * 4 + (w & 3)));
     const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t));
     s0 += f.x; s1 += f.y;
   }
@@ -277,16 +300,16 @@ template <int NV>
 __device__ __forceinline__ void load_chunk_bf16_finish(const ChunkRegs<NV>& g, float* v, const EpiCtx& ctx) {
   constexpr int U = NV / 8, ROWS_PER_IT = 32 / U;
   const int lane = threadIdx.x & 31;
-  uint4* patch = reinterpret_cast<uint4*>(ctx.patch);
+  const uint32_t patch = smem_addr(ctx.patch);
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int r = ROWS_PER_IT * j + lane / U, c = lane % U;
-    patch[r * U + (c ^ swz<NV>(r))] = g.q[j];
+    sts128(patch + 16 * (r * U + (c ^ swz<NV>(r))), g.q[j]);
   }
   __syncwarp();
 #pragma unroll
   for (int c = 0; c < U; ++c) {
-    const uint4 t = patch[lane * U + (c ^ swz<NV>(lane))];
+    const uint4 t = lds128(patch + 16 * (lane * U + (c ^ swz<NV>(lane))));
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -308,7 +331,8 @@ __device__ __forceinline__ void load_chunk_bf16_finish(const ChunkRegs<NV>& g, f
 // kernel before they wait for a tile's accumulator; stages the tile's bias values in shared memory.
 template <int BN>
 __device__ __forceinline__ void stage_bias(const float* bias, int n0, int N, float* sbias, int t, int nt) {
-  for (int i = t; i < BN; i += nt) sbias[i] = (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+  const uint32_t sb = smem_addr(sbias);
+  for (int i = t; i < BN; i += nt) sts32f(sb + 4 * i, (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f);
 }
 
 template <typename T, int NV> struct staged_io { static constexpr bool value = std::is_same<T, bf16>::value && (NV == 16 || NV == 32); };
@@ -353,14 +377,21 @@ struct EpiStore {
     constexpr bool STAGED = staged_io<OutT, NV>::value && MODE == EPI_PLAIN;
     if (!STAGED && !valid) return;
     float v[NV];
+    float bb[NV >= 16 ? NV : 1];
+    if constexpr (NV >= 16) {
+      const uint32_t sb = smem_addr(ctx.sbias);
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) { float4 t = lds128f(sb + 4 * i); bb[i] = t.x; bb[i + 1] = t.y; bb[i + 2] = t.z; bb[i + 3] = t.w; }
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if constexpr (NV >= 16) v[i] = fmaf(acc[i], scale, ctx.sbias[i]); else v[i] = fmaf(acc[i], scale, p.b[i]);
+      if constexpr (NV >= 16) v[i] = fmaf(acc[i], scale, bb[i]); else v[i] = fmaf(acc[i], scale, p.b[i]);
       if constexpr (MODE == EPI_ADDEND) v[i] += p.a[i];
       if (relu) v[i] = fmaxf(v[i], 0.f);
       if constexpr (MODE == EPI_ACCUM) v[i] += p.a[i];
-      if (STAGED && i >= nvalid) v[i] = 0.f;
     }
+    // columns >= nvalid need no masking on the staged path: their accumulators are exactly 0 (the B
+    // operand rows beyond N are zero-filled by TMA) and tile_begin staged a 0 bias for them.
     if constexpr (STAGED) {
       if (ctx.patch) {
         store_chunk_bf16<NV>(reinterpret_cast<bf16*>(out) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, v, nvalid, ctx);
@@ -421,10 +452,16 @@ struct EpiBCE {
     float d[NV];
     float ll = 0.f;
     const float wscale = p.w * inv_bg;
+    float bb[NV >= 16 ? NV : 1];
+    if constexpr (NV >= 16) {
+      const uint32_t sb = smem_addr(ctx.sbias);
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) { float4 t = lds128f(sb + 4 * i); bb[i] = t.x; bb[i + 1] = t.y; bb[i + 2] = t.z; bb[i + 3] = t.w; }
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float l;
-      if constexpr (NV >= 16) l = acc[i] + gen_bias + ctx.sbias[i]; else l = acc[i] + gen_bias + p.b[i];
+      if constexpr (NV >= 16) l = acc[i] + gen_bias + bb[i]; else l = acc[i] + gen_bias + p.b[i];
       float e, sp, inv1pe;
       if (fast) {
         // exp(-|l|) in (0,1]; log(1+e) with 1+e in (1,2]: absolute error of the intrinsics ~1e-7
@@ -500,7 +537,8 @@ struct EpiReluMask {
       float hv[NV];
       load_chunk_bf16_finish<NV>(p.g, hv, ctx);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = (hv[i] > 0.f && i < nvalid && valid) ? acc[i] : 0.f;
+      // rows >= M and columns >= N have zero accumulators (TMA zero fill), so only the mask is applied
+      for (int i = 0; i < NV; ++i) v[i] = hv[i] > 0.f ? acc[i] : 0.f;
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = (p.h[i] > 0.f && i < nvalid) ? acc[i] : 0.f;

@@ -333,6 +333,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
         if constexpr (CW == 32) tmem_ld32_issue(taddr + ci * CW, r); else tmem_ld16_issue(taddr + ci * CW, r);
         auto pre = epi.template prefetch<CW>(m, n, nv, m < M, ctx);   // global loads fly while TMEM is read
         if constexpr (CW == 32) tmem_ld32_wait(r); else tmem_ld16_wait(r);
+        if (tr && ci / 2 < 3) trace[16 * it + 13 + ci / 2] = clock64();
         float v[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
