@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 namespace gmvae {
 
@@ -34,6 +35,28 @@ void set_error(const std::string& msg);
     int _r = (expr);           \
     if (_r != 0) return _r;    \
   } while (0)
+
+// ----------------------------------------------------------------------------- launches
+// Programmatic dependent launch: every kernel of the step is launched with the
+// programmatic-stream-serialization attribute, so its CTAs may become resident (and run their
+// prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel drains.
+// Each kernel calls griddep_wait() before it touches global memory -- that returns only when the
+// previous grid has completed and its writes are visible -- and griddep_launch() right after, which
+// lets the next kernel's CTAs be scheduled as soon as SM resources free up.
+extern bool g_use_pdl;
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // ----------------------------------------------------------------------------- conversions
 template <typename T> __device__ __forceinline__ float to_f32(T v);

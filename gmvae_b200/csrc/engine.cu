@@ -25,6 +25,7 @@
 
 namespace gmvae {
 
+bool g_use_pdl = true;
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -415,8 +416,7 @@ static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, fl
   int rows_per_block = std::max(64, (M * col_blocks + 2 * 148 - 1) / (2 * 148));
   rows_per_block = round_up(rows_per_block, 8);
   dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<T><<<grid, 256, 0, st>>>(dY, ldy, M, N, rows_per_block, db);
-  GM_CHECK_CUDA(cudaGetLastError());
+  GM_CHECK_CUDA(launch_k(colsum_kernel<T>, grid, dim3(256), 0, st, true, dY, ldy, M, N, rows_per_block, db));
   GM_LAUNCHED(h, st, PC_BIAS_GRAD);
   return 0;
 }
@@ -523,17 +523,18 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   A* x_act = h->buf<A>("x_act");
   {
     const int64_t n = (int64_t)B * D;
-    if (D % 16 == 0) convert_x_kernel<A><<<(unsigned)((n / 16 + 255) / 256), 256, 0, st>>>(x_u8, x_act, n);
-    else convert_x_rows_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_u8, x_act, B, D, Dp);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_MISC);
+    // first kernel of the step: follows a memset node, launched with a full dependency
+    if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
+    else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp)); GM_LAUNCHED(h, st, PC_MISC);
   }
   const float* eps = eps_in; const float* u = u_in;
   if (!eps || (gm && !u)) {
     float* e = h->buf<float>("eps"); float* uu = gm ? h->buf<float>("u") : nullptr;
     int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
     int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
-    fill_noise_kernel<<<(unsigned)((q + 255) / 256), 256, 0, st>>>(e, ne, uu, nu, h->state, (uint64_t)h->rank);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_MISC);
+    GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, uu, nu,
+                           (const DeviceState*)h->state, (uint64_t)h->rank));
+    GM_LAUNCHED(h, st, PC_MISC);
     if (!eps) eps = e;
     if (gm && !u) u = uu;
   }
@@ -561,8 +562,8 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
-    head_y_fwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, u, B, K, 1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
+    GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, u, B, K,
+                           1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc)); GM_LAUNCHED(h, st, PC_HEADS);
     // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
     {
       const Linear& l = h->prior_gmm.layers[0];
@@ -607,17 +608,18 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   float* z_f32 = h->buf<float>("z_f32");
   {
     int64_t n = (int64_t)B * Z;
-    head_z_fwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, prior_mode, B, Z, c.raw_sigma_bias,
-                                                                    c.sigma_min, inv_bg, z_act, Zp, z_f32, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
+    GM_CHECK_CUDA(launch_k(head_z_fwd_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, true, (const float*)enc_out, eps,
+                           (const float*)prior_out, prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, z_act, Zp, z_f32, acc));
+    GM_LAUNCHED(h, st, PC_HEADS);
   }
   float* dz_prior = h->buf<float>("dz_prior");
   if (prior_mode == 1) {
     const int warps = 4;
-    gmp_prior_kernel<<<(B + warps - 1) / warps, warps * 32, warps * K * sizeof(float), st>>>(
-        z_f32, h->params + h->loc_off, h->params + h->raw_scale_off, h->params + h->mix_off, B, K, Z, inv_bg, dz_prior,
-        h->grads + h->loc_off, h->grads + h->raw_scale_off, h->grads + h->mix_off, acc);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
+    GM_CHECK_CUDA(launch_k(gmp_prior_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), warps * K * sizeof(float), st, true,
+                           (const float*)z_f32, (const float*)(h->params + h->loc_off), (const float*)(h->params + h->raw_scale_off),
+                           (const float*)(h->params + h->mix_off), B, K, Z, inv_bg, dz_prior, h->grads + h->loc_off,
+                           h->grads + h->raw_scale_off, h->grads + h->mix_off, acc));
+    GM_LAUNCHED(h, st, PC_HEADS);
   }
   // decoder: hidden layers, then logits fused with the Bernoulli log-likelihood (and db of that layer)
   bool dec_bias_fused = false;
@@ -643,13 +645,26 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   }
   GM_TRY(comm_bucket(h, st, h->bucket_end[0]));     // decoder gradients are final
   A* d_prior_out = h->buf<A>("d_prior_out");
+  bool enc_bias_fused = false;
   {
     int64_t n = (int64_t)B * Z;
-    head_z_bwd_kernel<A><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(enc_out, eps, prior_out, dz, dz_prior, prior_mode, B, Z,
-                                                                    c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, d_prior_out, Z2p);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
+    enc_bias_fused = Z <= 256 && !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    if (enc_bias_fused) {
+      // also reduces db of the last encoder layer and of prior_gmm over the batch
+      const int lanes = 256 / Z;
+      const int blocks = std::max(1, std::min(2 * tc::num_sms(), (B + lanes - 1) / lanes));
+      GM_CHECK_CUDA(launch_k(head_z_bwd_cs_kernel<A>, dim3(blocks), dim3(256), 4 * 256 * sizeof(float), st, true, (const float*)enc_out, eps,
+                             (const float*)prior_out, (const float*)dz, (const float*)dz_prior, prior_mode, B, Z, c.raw_sigma_bias,
+                             c.sigma_min, inv_bg, d_enc_out, d_prior_out, Z2p, h->grads + enc_last.b_off,
+                             gm ? h->grads + h->prior_gmm.layers[0].b_off : (float*)nullptr));
+    } else {
+      GM_CHECK_CUDA(launch_k(head_z_bwd_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, true, (const float*)enc_out, eps,
+                             (const float*)prior_out, (const float*)dz, (const float*)dz_prior, prior_mode, B, Z, c.raw_sigma_bias,
+                             c.sigma_min, inv_bg, d_enc_out, d_prior_out, Z2p));
+    }
+    GM_LAUNCHED(h, st, PC_HEADS);
   }
-  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st)));
+  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st, enc_bias_fused)));
   if (gm) {
     float* dy = h->buf<float>("dy"); A* dlogits_y = h->buf<A>("dlogits_y");
     LinView Ly = view(h, enc_l0, D, K);
@@ -666,25 +681,27 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       const Linear& l = h->prior_gmm.layers[0];
       LinView Lp = view(h, l);
       GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
-      GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
+      if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
       EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, d_prior_out, Z2p, B, Lp, e, st)));
     }
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
-    head_y_bwd_kernel<A><<<(B + 7) / 8, 256, 0, st>>>(logits_y, y_f32, dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_HEADS);
-    GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st)));
+    const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    GM_CHECK_CUDA(launch_k(head_y_bwd_kernel<A>, dim3(std::max(1, std::min(2 * tc::num_sms(), (B + 7) / 8))), dim3(256), 0, st, true,
+                           (const float*)logits_y, (const float*)y_f32, (const float*)dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp,
+                           ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
+    GM_LAUNCHED(h, st, PC_HEADS);
+    GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st, ey_bias_fused)));
   }
   return 0;
 }
 
 static int refresh_shadows(gmvae_handle* h, bool bump, cudaStream_t st) {
   if (h->shadow_tiles > 0) {
-    refresh_shadows_kernel<<<h->shadow_tiles, dim3(32, 8), 0, st>>>(h->shadow_dev, (int)h->shadow_host.size(), h->state, bump ? 1 : 0);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
+    GM_CHECK_CUDA(launch_k(refresh_shadows_kernel, dim3(h->shadow_tiles), dim3(32, 8), 0, st, true, (const ShadowEntry*)h->shadow_dev,
+                           (int)h->shadow_host.size(), h->state, bump ? 1 : 0)); GM_LAUNCHED(h, st, PC_ADAM);
   } else if (bump) {
-    bump_step_kernel<<<1, 1, 0, st>>>(h->state);
-    GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
+    GM_CHECK_CUDA(launch_k(bump_step_kernel, dim3(1), dim3(1), 0, st, true, h->state)); GM_LAUNCHED(h, st, PC_ADAM);
   }
   return 0;
 }
@@ -730,6 +747,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   h->cfg = *cfg;
   const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
   h->debug_flags = dbg ? atoi(dbg) : 0;
+  g_use_pdl = !(h->debug_flags & 128);
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
   DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull;
@@ -810,20 +828,26 @@ int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int 
 int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
   GM_TRY(check_ready(h));
   GM_REQUIRE(loss_terms != nullptr, "null loss_terms");
-  finalize_loss_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->grads + h->n_params, loss_terms);
-  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, (cudaStream_t)stream, PC_MISC);
+  GM_CHECK_CUDA(launch_k(finalize_loss_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, false, (const float*)(h->grads + h->n_params), loss_terms)); GM_LAUNCHED(h, (cudaStream_t)stream, PC_MISC);
   return 0;
+}
+
+// Adam (+ optionally the loss-term finalisation, folded into the same launch by gmvae_train_step)
+static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st) {
+  const gmvae_config& c = h->cfg;
+  int64_t n = h->n_params;
+  // after a cross-stream join (data-parallel all-reduce) the kernel is launched with a full dependency
+  const bool pdl = !(h->comm && h->world > 1);
+  GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n / 4 + 255) / 256 + 1)), dim3(256), 0, st, pdl, h->params, (const float*)h->grads,
+                         h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, (const DeviceState*)h->state,
+                         (const float*)(h->grads + h->n_params), loss_terms));
+  GM_LAUNCHED(h, st, PC_ADAM);
+  return refresh_shadows(h, true, st);
 }
 
 int gmvae_adam_step(gmvae_handle* h, void* stream) {
   GM_TRY(check_ready(h));
-  cudaStream_t st = (cudaStream_t)stream;
-  const gmvae_config& c = h->cfg;
-  int64_t n = h->n_params;
-  adam_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, n, c.learning_rate,
-                                                                  c.beta1, c.beta2, c.epsilon, h->state);
-  GM_CHECK_CUDA(cudaGetLastError()); GM_LAUNCHED(h, st, PC_ADAM);
-  return refresh_shadows(h, true, st);
+  return adam_step_impl(h, nullptr, (cudaStream_t)stream);
 }
 
 int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream) {
@@ -896,8 +920,7 @@ int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global
   if (r == 0) r = gmvae_allreduce_grads(h, stream);
   h->overlap_comm = false;
   GM_TRY(r);
-  if (loss_terms) GM_TRY(gmvae_finalize_loss(h, loss_terms, stream));
-  return gmvae_adam_step(h, stream);
+  return adam_step_impl(h, loss_terms, (cudaStream_t)stream);
 }
 
 int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
@@ -945,8 +968,8 @@ int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int6
   if (!u) n_u = 0;
   int64_t q = (n_eps + 3) / 4 + (n_u + 3) / 4;
   if (q == 0) return 0;
-  fill_noise_kernel<<<(unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eps, n_eps, u, n_u, h->state, (uint64_t)h->rank);
-  GM_CHECK_CUDA(cudaGetLastError());
+  GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, eps, n_eps, u, n_u,
+                         (const DeviceState*)h->state, (uint64_t)h->rank));
   return 0;
 }
 

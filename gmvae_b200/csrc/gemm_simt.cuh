@@ -22,6 +22,8 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sAm, int64_t sAk, const TB* _
                  int64_t sBn, int M, int N, int K, int k_per_split, Epi epi_in) {
   __shared__ float As[SIMT_BK][SIMT_BM + 4];
   __shared__ float Bs[SIMT_BK][SIMT_BN + 4];
+  griddep_wait();
+  griddep_launch();
   Epi epi = epi_in;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
@@ -85,8 +87,7 @@ inline cudaError_t launch_gemm_simt(const TA* A, int64_t sAm, int64_t sAk, const
   k_per = (k_per + SIMT_BK - 1) / SIMT_BK * SIMT_BK;
   split_k = (K + k_per - 1) / k_per;
   dim3 grid((N + SIMT_BN - 1) / SIMT_BN, (M + SIMT_BM - 1) / SIMT_BM, split_k);
-  gemm_simt_kernel<TA, TB, Epi><<<grid, SIMT_THREADS, 0, st>>>(A, sAm, sAk, B, sBk, sBn, M, N, K, k_per, epi);
-  return cudaGetLastError();
+  return launch_k(gemm_simt_kernel<TA, TB, Epi>, grid, dim3(SIMT_THREADS), 0, st, true, A, sAm, sAk, B, sBk, sBn, M, N, K, k_per, epi);
 }
 
 }  // namespace gmvae

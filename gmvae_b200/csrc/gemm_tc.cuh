@@ -229,6 +229,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on global memory written by it is read.
+  griddep_wait();
+  griddep_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -406,8 +410,8 @@ int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, cons
   split_k = (kb_total + per - 1) / per;
   const int total = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M) * split_k;
   const int grid = persistent ? std::min(total, num_sms()) : total;
-  kern<<<grid, NUM_THREADS2, smem_bytes<BLOCK_N>(), st>>>(maps, M, N, kb1, kb2, per, split_k, g_trace, epi);
-  GM_CHECK_CUDA(cudaGetLastError());
+  GM_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(NUM_THREADS2), (size_t)smem_bytes<BLOCK_N>(), st, true, maps, M, N, kb1, kb2, per, split_k,
+                         g_trace, epi));
   return 0;
 }
 

@@ -18,6 +18,8 @@ struct DeviceState {           // owned by the handle, lives on the device
 // ---- x: bool bytes -> GEMM operand type (vae.py:75, gmvae.py:86,104: tf.cast(x, float32)) ----
 template <typename T>
 __global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n) {
+  griddep_wait();
+  griddep_launch();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
   if (i + 16 <= n) {
     uint4 t = *reinterpret_cast<const uint4*>(x + i);
@@ -37,6 +39,8 @@ __global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ 
 // generic variant: rows of D bytes -> rows of ld elements (ld >= D; padding left untouched)
 template <typename T>
 __global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int B, int D, int ld) {
+  griddep_wait();
+  griddep_launch();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (int64_t)B * D) {
     int64_t r = i / D, c = i % D;
@@ -49,6 +53,8 @@ __global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restri
 // (RelaxedOneHotCategorical.sample).  Keyed by (seed, step, stream id, element index).
 __global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
                                   const DeviceState* st, uint64_t rank_stream) {
+  griddep_wait();
+  griddep_launch();
   const uint64_t seed = st->seed, step = (uint64_t)st->step;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t q_eps = (n_eps + 3) / 4, q_u = (n_u + 3) / 4;
@@ -79,6 +85,8 @@ template <typename ActT>
 __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ u, int B, int K, float inv_T,
                                   float inv_bg, float* __restrict__ y_f32, ActT* __restrict__ y_act, int ld_yact,
                                   float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float scratch[32];
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -129,10 +137,15 @@ __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float*
 template <typename ActT>
 __global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y_f32,
                                   const float* __restrict__ dy, int B, int K, float inv_T, float inv_bg,
-                                  ActT* __restrict__ dlogits, int ld_out) {
+                                  ActT* __restrict__ dlogits, int ld_out, float* __restrict__ db) {
+  griddep_wait();
+  griddep_launch();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= B) return;
+  const int wpb = blockDim.x >> 5;
+  float cs[HEAD_MAXK / 32];                            // per-lane column sums (bias gradient of encoder_y's last layer)
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i) cs[i] = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
   float l[HEAD_MAXK / 32], y[HEAD_MAXK / 32], g[HEAD_MAXK / 32];
   float ml = -INFINITY, ydy = 0.f;
 #pragma unroll
@@ -164,9 +177,19 @@ __global__ void head_y_bwd_kernel(const float* __restrict__ logits, const float*
     int k = lane + 32 * i;
     if (k < K) {
       float lp = l[i] - lse;
-      dlogits[(int64_t)row * ld_out + k] = from_f32<ActT>(y[i] * (g[i] - ydy) * inv_T + expf(lp) * (lp - plogp) * inv_bg);
+      ActT o = from_f32<ActT>(y[i] * (g[i] - ydy) * inv_T + expf(lp) * (lp - plogp) * inv_bg);
+      dlogits[(int64_t)row * ld_out + k] = o;
+      cs[i] += to_f32<ActT>(o);
     } else if (k < ld_out) {
       dlogits[(int64_t)row * ld_out + k] = from_f32<ActT>(0.f);
+    }
+  }
+  }
+  if (db) {
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      if (k < K && cs[i] != 0.f) atomicAdd(db + k, cs[i]);
     }
   }
 }
@@ -183,6 +206,8 @@ __global__ void head_z_fwd_kernel(const float* __restrict__ enc_out, const float
                                   const float* __restrict__ prior_out, int prior_mode, int B, int Z, float c,
                                   float sigma_min, float inv_bg, ActT* __restrict__ z_act, int ld_z, float* __restrict__ z_f32,
                                   float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float scratch[32];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float kl = 0.f;
@@ -219,6 +244,8 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
                                   const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c,
                                   float sigma_min, float inv_bg, ActT* __restrict__ d_enc_out,
                                   ActT* __restrict__ d_prior_out, int ld_out) {
+  griddep_wait();
+  griddep_launch();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * Z) return;
   int b = (int)(i / Z), j = (int)(i % Z);
@@ -248,6 +275,69 @@ __global__ void head_z_bwd_kernel(const float* __restrict__ enc_out, const float
   d_enc_out[(int64_t)b * ld_out + Z + j] = from_f32<ActT>(spq >= sigma_min ? dsg * sigmoid_f(raw + c) : 0.f);
 }
 
+// Persistent variant of head_z_bwd that also reduces the bias gradients of the last encoder layer
+// (and of prior_gmm) over the batch: thread <-> latent dimension j, row lanes stride over the batch,
+// one shared-memory reduction and 2-4 atomics per column per block.  Requires Z <= blockDim.x.
+template <typename ActT>
+__global__ void head_z_bwd_cs_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
+                                     const float* __restrict__ prior_out, const float* __restrict__ dz_dec,
+                                     const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c, float sigma_min,
+                                     float inv_bg, ActT* __restrict__ d_enc_out, ActT* __restrict__ d_prior_out, int ld_out,
+                                     float* __restrict__ db_enc, float* __restrict__ db_prior) {
+  griddep_wait();
+  griddep_launch();
+  extern __shared__ float red[];                       // [4][blockDim.x]
+  const int lanes = blockDim.x / Z;                    // row lanes per block
+  const int j = threadIdx.x % Z, rl = threadIdx.x / Z;
+  float s_mu = 0.f, s_raw = 0.f, s_pmu = 0.f, s_praw = 0.f;
+  if (rl < lanes) {
+    for (int b = blockIdx.x * lanes + rl; b < B; b += gridDim.x * lanes) {
+      const int64_t i = (int64_t)b * Z + j;
+      float mu = enc_out[(int64_t)b * 2 * Z + j], raw = enc_out[(int64_t)b * 2 * Z + Z + j];
+      float spq = softplus_f(raw + c);
+      float sg = fmaxf(spq, sigma_min);
+      float e = eps[i];
+      float z = fmaf(sg, e, mu);
+      float dz = dz_dec[i];
+      if (prior_mode == 0) {
+        dz += z * inv_bg;
+      } else if (prior_mode == 1) {
+        dz += dz_prior[i];
+      } else {
+        float mp = prior_out[(int64_t)b * 2 * Z + j], rp = prior_out[(int64_t)b * 2 * Z + Z + j];
+        float spp = softplus_f(rp + c);
+        float sp = fmaxf(spp, sigma_min);
+        float d = z - mp;
+        float isp2 = 1.f / (sp * sp);
+        dz += d * isp2 * inv_bg;
+        float dsp = (1.f / sp - d * d * isp2 / sp) * inv_bg;
+        ActT a0 = from_f32<ActT>(-d * isp2 * inv_bg), a1 = from_f32<ActT>(spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f);
+        d_prior_out[(int64_t)b * ld_out + j] = a0; d_prior_out[(int64_t)b * ld_out + Z + j] = a1;
+        s_pmu += to_f32<ActT>(a0); s_praw += to_f32<ActT>(a1);          // sums of the values as stored
+      }
+      float dsg = dz * e - inv_bg / sg;
+      ActT g0 = from_f32<ActT>(dz), g1 = from_f32<ActT>(spq >= sigma_min ? dsg * sigmoid_f(raw + c) : 0.f);
+      d_enc_out[(int64_t)b * ld_out + j] = g0; d_enc_out[(int64_t)b * ld_out + Z + j] = g1;
+      s_mu += to_f32<ActT>(g0); s_raw += to_f32<ActT>(g1);
+    }
+  }
+  const int n = blockDim.x;
+  red[threadIdx.x] = s_mu; red[n + threadIdx.x] = s_raw; red[2 * n + threadIdx.x] = s_pmu; red[3 * n + threadIdx.x] = s_praw;
+  __syncthreads();
+  if (threadIdx.x < Z) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t0 += red[l * Z + j]; t1 += red[n + l * Z + j]; t2 += red[2 * n + l * Z + j]; t3 += red[3 * n + l * Z + j];
+    }
+    if (t0 != 0.f) atomicAdd(db_enc + j, t0);
+    if (t1 != 0.f) atomicAdd(db_enc + Z + j, t1);
+    if (prior_mode == 2) {
+      if (t2 != 0.f) atomicAdd(db_prior + j, t2);
+      if (t3 != 0.f) atomicAdd(db_prior + Z + j, t3);
+    }
+  }
+}
+
 // ---- VAE_GMP mixture prior (vae.py:231-244, 181): forward value and every gradient -------------
 // log p(z) = logsumexp_k [ log_softmax(m)_k + log N(z; loc_k, softplus(raw_scale_k)) ]
 // One warp per row; lanes stride over Z.  Adds -log p / B to the KL accumulator, writes
@@ -256,6 +346,8 @@ __global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __res
                                  const float* __restrict__ raw_scale, const float* __restrict__ mix_logits, int B, int K,
                                  int Z, float inv_bg, float* __restrict__ dz_prior, float* __restrict__ d_loc,
                                  float* __restrict__ d_raw_scale, float* __restrict__ d_mix, float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
   extern __shared__ float sm[];  // per warp: K log-weights
   __shared__ float scratch[32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -314,6 +406,8 @@ __global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __res
 // 256 columns x `rows_per_block` rows with 8 row-lanes, reduced through shared memory.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, int M, int N, int rows_per_block, float* __restrict__ db) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float sm[8][32][9];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n0 = blockIdx.x * 256 + tx * 8;
@@ -345,6 +439,8 @@ __global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, int M, int N
 
 // ---- loss terms ---------------------------------------------------------------------------------
 __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
   if (threadIdx.x == 0) {
     float nll = acc[ACC_NLL], kl = acc[ACC_KL], ne = acc[ACC_NENT];
     out[0] = nll + kl + ne;  // gmvae.py:267 / vae.py:185
@@ -356,8 +452,15 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __res
 // lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // theta -= lr_t m / (sqrt(v) + eps).   t = step+1 read from the device; one flat pass.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr, float b1, float b2, float eps, const DeviceState* st) {
+                            int64_t n, float lr, float b1, float b2, float eps, const DeviceState* st,
+                            const float* __restrict__ acc, float* __restrict__ loss_out) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float lr_t_s;
+  if (loss_out && blockIdx.x == 0 && threadIdx.x == 32) {   // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
+    float nll = acc[ACC_NLL], kl = acc[ACC_KL], ne = acc[ACC_NENT];
+    loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
+  }
   if (threadIdx.x == 0) {
     double t = (double)(st->step + 1);
     lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
@@ -396,6 +499,8 @@ struct ShadowEntry {
   int tiles_x, tile_begin;   // tiles along cols; first flat tile index of this entry
 };
 __global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, int n_entries, DeviceState* st, int bump_step) {
+  griddep_wait();
+  griddep_launch();
   __shared__ float tile[32][33];
   if (bump_step && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) st->step += 1;
   int e = 0;
@@ -417,6 +522,8 @@ __global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, 
     }
   }
 }
-__global__ void bump_step_kernel(DeviceState* st) { st->step += 1; }
+__global__ void bump_step_kernel(DeviceState* st) {
+  griddep_wait();
+  griddep_launch(); st->step += 1; }
 
 }  // namespace gmvae
