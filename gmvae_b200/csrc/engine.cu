@@ -147,6 +147,7 @@ struct gmvae_handle {
   bool overlap_comm = false;             // set by gmvae_train_step
   int64_t reduced_upto = 0;              // floats of `grads` already handed to NCCL this step
   int64_t bucket_end[2] = {0, 0};        // flat offsets where bucket 0 (decoder) / 1 (encoder, prior) end
+  int chunk_samples = 0;                 // objective M: samples per chunk of per-component rows
   // graph
   cudaGraphExec_t graph_exec = nullptr;
 
@@ -232,10 +233,21 @@ static int plan(gmvae_handle* h) {
     build_mlp(h, h->encoder, "encoder", D, with(2 * Z));
   }
   // ---- workspace ----
-  const size_t B = (size_t)c.max_batch, asz = h->act_size();
+  const size_t Bfull = (size_t)c.max_batch, asz = h->act_size();
   const int Kp = round_up(K, 8);
-  plan_buf(h, "x_act", B * round_up(D, 8) * asz);
-  plan_buf(h, "eps", B * Z * 4);
+  // Objective M evaluates K components per sample: rows r = b*K + k, processed in chunks of whole
+  // samples so that the per-component activations never exceed `rows_cap` rows.
+  h->chunk_samples = (int)Bfull;
+  if (c.objective == GMVAE_OBJECTIVE_MARGINAL) {
+    const char* env = getenv("GMVAE_M_CHUNK_ROWS");
+    long max_rows = env ? atol(env) : 131072;
+    long bc = std::max(1L, max_rows / K);
+    if (bc > 64) bc = bc / 64 * 64;
+    h->chunk_samples = (int)std::min<long>((long)Bfull, bc);
+  }
+  const size_t B = c.objective == GMVAE_OBJECTIVE_MARGINAL ? (size_t)h->chunk_samples * K : Bfull;   // row capacity
+  plan_buf(h, "x_act", Bfull * round_up(D, 8) * asz);
+  plan_buf(h, "eps", Bfull * (c.objective == GMVAE_OBJECTIVE_MARGINAL ? K : 1) * Z * 4);
   plan_buf(h, "dec.dlogits", B * round_up(D, 8) * asz);
   plan_buf(h, "dz", B * Z * 4);
   plan_buf(h, "enc_out", B * 2 * Z * 4);
@@ -244,16 +256,26 @@ static int plan(gmvae_handle* h) {
   plan_mlp_bufs(h, h->decoder, B, asz);
   plan_mlp_bufs(h, h->encoder, B, asz);
   if (c.model == GMVAE_MODEL_GMVAE) {
-    plan_mlp_bufs(h, h->encoder_y, B, asz);
-    plan_buf(h, "u", B * K * 4);
-    plan_buf(h, "logits_y", B * K * 4);
-    plan_buf(h, "y_f32", B * K * 4);
-    plan_buf(h, "y_act", B * Kp * asz);
-    plan_buf(h, "prior_out", B * 2 * Z * 4);
-    plan_buf(h, "d_prior_out", B * round_up(2 * Z, 8) * asz);
-    plan_buf(h, "dy", B * K * 4);
-    plan_buf(h, "dlogits_y", B * Kp * asz);
-    plan_buf(h, "pre_y", B * (size_t)(h->hidden.empty() ? 2 * Z : h->hidden[0]) * 4);
+    plan_mlp_bufs(h, h->encoder_y, Bfull, asz);
+    plan_buf(h, "u", Bfull * K * 4);
+    plan_buf(h, "logits_y", Bfull * K * 4);
+    plan_buf(h, "y_f32", Bfull * K * 4);
+    plan_buf(h, "y_act", Bfull * Kp * asz);
+    plan_buf(h, "dlogits_y", Bfull * Kp * asz);
+    const size_t H0 = (size_t)(h->hidden.empty() ? 2 * Z : h->hidden[0]);
+    if (c.objective == GMVAE_OBJECTIVE_MARGINAL) {
+      plan_buf(h, "tab", (size_t)K * 2 * Z * 4);
+      plan_buf(h, "dtab", (size_t)K * 2 * Z * 4);
+      plan_buf(h, "xproj", Bfull * H0 * 4);
+      plan_buf(h, "dxproj", Bfull * round_up((int)H0, 8) * asz);
+      plan_buf(h, "rec", Bfull * K * 8);
+      plan_buf(h, "klrow", Bfull * K * 4);
+    } else {
+      plan_buf(h, "prior_out", Bfull * 2 * Z * 4);
+      plan_buf(h, "d_prior_out", Bfull * round_up(2 * Z, 8) * asz);
+      plan_buf(h, "dy", Bfull * K * 4);
+      plan_buf(h, "pre_y", Bfull * H0 * 4);
+    }
   }
   if (c.model == GMVAE_MODEL_VAE_GMP) {
     plan_buf(h, "z_f32", B * Z * 4);
@@ -462,7 +484,7 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
 // is the bias gradient of layer i-1 (no separate pass over dh).
 template <typename A, typename TD>
 static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols,
-                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false) {
+                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false, int min_layer = 0) {
   const int nl = (int)m.layers.size();
   const bool fuse = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
   bool bias_done = dout_bias_done;   // bias gradient of the layer whose output gradient we hold
@@ -478,13 +500,14 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
     if (!first) {
       LinView Lf = view(h, l);
       const int64_t ldh = ldp(m.layers[nl - 2].out);
-      float* cs = (fuse && tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf)) ? h->grads + m.layers[nl - 2].b_off : nullptr;
+      // (layers below min_layer get their bias gradient from the caller)
+      float* cs = (fuse && nl - 2 >= min_layer && tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf)) ? h->grads + m.layers[nl - 2].b_off : nullptr;
       EpiReluMask<A, A> epi{b.dhid[nl - 2], ldh, b.hid[nl - 2], ldh, cs};
       GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
       bias_done = cs != nullptr;
     }
   }
-  for (int i = nl - 2; i >= 0; --i) {
+  for (int i = nl - 2; i >= min_layer; --i) {
     const Linear& l = m.layers[i];
     const bool first = i == 0;
     LinView L = view(h, l, 0, first ? in0_cols : -1);
@@ -497,7 +520,7 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
     if (!first) {
       LinView Lf = view(h, l);
       const int64_t ldh = ldp(m.layers[i - 1].out);
-      float* cs = (fuse && tc_ok_dgrad<A>(h, b.dhid[i], ldd, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
+      float* cs = (fuse && i - 1 >= min_layer && tc_ok_dgrad<A>(h, b.dhid[i], ldd, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
       EpiReluMask<A, A> epi{b.dhid[i - 1], ldh, b.hid[i - 1], ldh, cs};
       GM_TRY((lin_dgrad<A>(h, b.dhid[i], ldd, M, Lf, epi, st)));
       bias_done = cs != nullptr;
@@ -630,7 +653,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     const int64_t ldin = nl == 1 ? Zp : hid_ld(nl - 2);
     LinView Ld = view(h, l);
     dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, in, ldin, Ld);
-    EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, nullptr,
+    EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, (double*)nullptr,
                   acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
     GM_TRY(lin_fwd<A>(h, in, ldin, B, Ld, epi, st));
   }
@@ -696,6 +719,157 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   return 0;
 }
 
+
+// ============================================================================ objective M
+// K-way marginalised ELBO (north_star (1)-(2)):
+//   pi = softmax(encoder_y(x));  for every component k (y = e_k):
+//     h1_k = relu(x W1[:D] + W1[D+k] + b1)   -- x-projection computed ONCE per sample, broadcast over k
+//     (mu_q, s_q)_k = rest of encoder_gmm;  z_k = mu_q + s_q eps_k;  rec_k = log p(x | z_k)
+//     KL_k = KL(N(mu_q, s_q) || prior_gmm(e_k))  (analytic)
+//   loss = mean_b sum_k pi_k (KL_k - rec_k) + mean_b sum_k pi_k log pi_k
+// The per-component rows (r = b*K + k) run through the SAME GEMM kernels as objective R, in
+// chunks of whole samples; weight gradients accumulate across chunks in the flat gradient buffer.
+template <typename A>
+static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in, cudaStream_t st) {
+  const gmvae_config& c = h->cfg;
+  const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
+  const int Dp = ldp(D), Zp = ldp(Z), Z2p = ldp(2 * Z), Kp = ldp(K);
+  const float inv_bg = 1.f / (float)Bg;
+  float* acc = h->grads + h->n_params;
+  if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
+  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  h->reduced_upto = 0;
+  double* rec = h->buf<double>("rec"); float* klrow = h->buf<float>("klrow");
+  float* tab = h->buf<float>("tab"); float* dtab = h->buf<float>("dtab");
+  GM_CHECK_CUDA(cudaMemsetAsync(rec, 0, (size_t)B * K * 8, st));
+  GM_CHECK_CUDA(cudaMemsetAsync(dtab, 0, (size_t)K * 2 * Z * 4, st));
+
+  A* x_act = h->buf<A>("x_act");
+  {
+    const int64_t n = (int64_t)B * D;
+    if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
+    else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp));
+    GM_LAUNCHED(h, st, PC_MISC);
+  }
+  const float* eps = eps_in;
+  if (!eps) {
+    float* e = h->buf<float>("eps");
+    const int64_t ne = (int64_t)B * K * Z, q = (ne + 3) / 4;
+    GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, (float*)nullptr, (int64_t)0,
+                           (const DeviceState*)h->state, (uint64_t)h->rank));
+    GM_LAUNCHED(h, st, PC_MISC);
+    eps = e;
+  }
+  MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder), enc = mlp_bufs<A>(h, h->encoder), ey = mlp_bufs<A>(h, h->encoder_y);
+  float* enc_out = h->buf<float>("enc_out"); A* d_enc_out = h->buf<A>("d_enc_out");
+  A* z_act = h->buf<A>("z_act"); float* dz = h->buf<float>("dz"); A* dlogits_x = h->buf<A>("dec.dlogits");
+  float* logits_y = h->buf<float>("logits_y"); float* pi = h->buf<float>("y_f32"); A* y_act = h->buf<A>("y_act");
+  float* xproj = h->buf<float>("xproj"); A* dxproj = h->buf<A>("dxproj"); A* dlogits_y = h->buf<A>("dlogits_y");
+  const Linear& enc_l0 = h->encoder.layers[0];
+  const Linear& enc_last = h->encoder.layers[nl - 1];
+  const Linear& prior = h->prior_gmm.layers[0];
+  const int H0 = enc_l0.out, H0p = ldp(H0);
+  auto hid_ld = [&](int i) { return (int64_t)ldp(h->hidden[i]); };
+
+  // ---- q(y|x) on the whole batch: pi = softmax(logits), nent
+  GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, Dp, D, B, 0, st));
+  {
+    const Linear& l = h->encoder_y.layers[nl - 1];
+    EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, ey.hid[nl - 2], hid_ld(nl - 2), B, view(h, l), epi, st));
+  }
+  GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, (const float*)nullptr, B, K,
+                         1.f, inv_bg, pi, y_act, Kp, acc));
+  GM_LAUNCHED(h, st, PC_HEADS);
+  // ---- prior table p(z | y = e_k), k = 0..K-1
+  GM_CHECK_CUDA(launch_k(prior_table_kernel, dim3((K * 2 * Z + 255) / 256), dim3(256), 0, st, true, (const float*)(h->params + prior.w_off),
+                         (const float*)(h->params + prior.b_off), K, 2 * Z, tab));
+  GM_LAUNCHED(h, st, PC_HEADS);
+  // ---- shared x-projection of encoder_gmm layer 0 (no bias, no activation), fp32
+  {
+    EpiStore<float> epi{xproj, (int64_t)H0, nullptr, nullptr, 0, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, x_act, Dp, B, view(h, enc_l0, 0, D), epi, st));
+  }
+  const float* Wy = h->params + enc_l0.w_off + (int64_t)D * H0;     // rows D..D+K-1 of W1
+
+  for (int b0 = 0; b0 < B; b0 += h->chunk_samples) {
+    const int nb = std::min(h->chunk_samples, B - b0), R = nb * K, row0 = b0 * K;
+    // h1 for all components of the chunk
+    {
+      const int64_t work = (int64_t)R * (H0 / 4);
+      GM_REQUIRE(H0 % 4 == 0, "objective=marginal needs hidden sizes that are multiples of 4");
+      const int blocks = (int)std::min<int64_t>((work + 255) / 256, 16 * tc::num_sms());
+      GM_CHECK_CUDA(launch_k(expand_h1_kernel<A>, dim3(blocks), dim3(256), 0, st, true, (const float*)(xproj + (int64_t)b0 * H0), (int64_t)H0, Wy,
+                             (const float*)(h->params + enc_l0.b_off), R, K, H0, enc.hid[0], (int64_t)H0p));
+      GM_LAUNCHED(h, st, PC_HEADS);
+    }
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, R, 1, st));
+    {
+      EpiStore<float> epi{enc_out, (int64_t)2 * Z, h->params + enc_last.b_off, nullptr, 0, 0, 1.f};
+      GM_TRY(lin_fwd<A>(h, enc.hid[nl - 2], hid_ld(nl - 2), R, view(h, enc_last), epi, st));
+    }
+    GM_CHECK_CUDA(launch_k(head_z_m_fwd_kernel<A>, dim3(std::max(1, std::min(4 * tc::num_sms(), (R + 7) / 8))), dim3(256), 0, st, true,
+                           (const float*)enc_out, eps, (const float*)tab, (const float*)pi, row0, R, K, Z, c.raw_sigma_bias, c.sigma_min,
+                           inv_bg, z_act, Zp, klrow, acc));
+    GM_LAUNCHED(h, st, PC_HEADS);
+    // decoder on every component row; Bernoulli log-likelihood weighted by pi, rec[r] kept for d/d pi
+    GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Zp, Z, R, 0, st));
+    bool dec_bias_fused = false;
+    {
+      const Linear& l = h->decoder.layers[nl - 1];
+      LinView Ld = view(h, l);
+      dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, dec.hid[nl - 2], hid_ld(nl - 2), Ld);
+      EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8 + (int64_t)b0 * D, (int64_t)D, K, pi + row0, rec + row0,
+                    acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
+      GM_TRY(lin_fwd<A>(h, dec.hid[nl - 2], hid_ld(nl - 2), R, Ld, epi, st));
+    }
+    GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, R, st, dec_bias_fused)));
+    {
+      const Linear& l0 = h->decoder.layers[0];
+      EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 1.f};
+      GM_TRY((lin_dgrad<A>(h, dec.dhid[0], hid_ld(0), R, view(h, l0), epi, st)));
+    }
+    {
+      const int lanes = 256 / Z;
+      const int blocks = std::max(1, std::min(2 * tc::num_sms(), (R + lanes - 1) / lanes));
+      const size_t smem = (size_t)(2 * 256 + K * 2 * Z) * sizeof(float);
+      GM_CHECK_CUDA(launch_k(head_z_m_bwd_kernel<A>, dim3(blocks), dim3(256), smem, st, true, (const float*)enc_out, eps, (const float*)tab,
+                             (const float*)pi, (const float*)dz, row0, R, K, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, Z2p,
+                             h->grads + enc_last.b_off, dtab));
+      GM_LAUNCHED(h, st, PC_HEADS);
+    }
+    // encoder_gmm layers >= 1 backward (layer 0 is handled through the shared x-projection)
+    GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, R, st, true, 1)));
+    {
+      const int col_blocks = (H0 + 63) / 64;
+      int spb = std::max(4, (nb * col_blocks + 2 * tc::num_sms() - 1) / (2 * tc::num_sms()));
+      dim3 grid(col_blocks, (nb + spb - 1) / spb);
+      static bool attr = false;
+      if (!attr) {
+        GM_CHECK_CUDA(cudaFuncSetAttribute(reduce_k_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * HEAD_MAXK * 64 * (int)sizeof(float)));
+        attr = true;
+      }
+      GM_CHECK_CUDA(launch_k(reduce_k_kernel<A>, grid, dim3(256), (size_t)4 * K * 64 * sizeof(float), st, true, (const A*)enc.dhid[0], (int64_t)H0p,
+                             b0, nb, K, H0, dxproj, (int64_t)H0p, h->grads + enc_l0.w_off + (int64_t)D * H0, h->grads + enc_l0.b_off, spb));
+      GM_LAUNCHED(h, st, PC_BIAS_GRAD);
+    }
+  }
+  GM_TRY(comm_bucket(h, st, h->bucket_end[0]));     // decoder gradients are final
+  // x-part of encoder_gmm layer 0: dW1[:D] = x^T dxproj over the whole batch
+  GM_TRY((lin_wgrad<A, A>(h, x_act, Dp, dxproj, H0p, B, view(h, enc_l0, 0, D), st)));
+  GM_CHECK_CUDA(launch_k(prior_table_bwd_kernel, dim3((2 * Z + 127) / 128), dim3(128), 0, st, true, (const float*)dtab, K, 2 * Z,
+                         h->grads + prior.w_off, h->grads + prior.b_off));
+  GM_LAUNCHED(h, st, PC_HEADS);
+  GM_TRY(comm_bucket(h, st, h->bucket_end[1]));     // encoder_gmm and prior_gmm gradients are final
+  const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+  GM_CHECK_CUDA(launch_k(head_y_m_bwd_kernel<A>, dim3(std::max(1, std::min(2 * tc::num_sms(), (B + 7) / 8))), dim3(256), 0, st, true,
+                         (const float*)logits_y, (const float*)pi, (const double*)rec, (const float*)klrow, B, K, inv_bg, dlogits_y, Kp,
+                         ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
+  GM_LAUNCHED(h, st, PC_HEADS);
+  GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st, ey_bias_fused)));
+  return 0;
+}
+
 static int refresh_shadows(gmvae_handle* h, bool bump, cudaStream_t st) {
   if (h->shadow_tiles > 0) {
     GM_CHECK_CUDA(launch_k(refresh_shadows_kernel, dim3(h->shadow_tiles), dim3(32, 8), 0, st, true, (const ShadowEntry*)h->shadow_dev,
@@ -731,7 +905,8 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   if (cfg->model != GMVAE_MODEL_VAE)
     GM_REQUIRE(cfg->mixture_components >= 1 && cfg->mixture_components <= HEAD_MAXK, "mixture_components must be in [1,128]");
   GM_REQUIRE(cfg->objective == GMVAE_OBJECTIVE_REFERENCE || cfg->model == GMVAE_MODEL_GMVAE, "objective applies to GMVAE only");
-  GM_REQUIRE(cfg->objective == GMVAE_OBJECTIVE_REFERENCE, "objective=marginal is not built yet");
+  if (cfg->objective == GMVAE_OBJECTIVE_MARGINAL)
+    GM_REQUIRE(cfg->num_hidden >= 1 && cfg->latent_size <= 256, "objective=marginal needs at least one hidden layer and latent_size <= 256");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -821,6 +996,10 @@ int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int 
   GM_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "batch must be in [1, max_batch]");
   GM_REQUIRE(global_batch >= batch, "global_batch must be >= batch");
   GM_REQUIRE(aligned16(x_u8), "x must be 16-byte aligned");
+  if (h->cfg.objective == GMVAE_OBJECTIVE_MARGINAL) {
+    if (h->bf16_mode()) return forward_backward_marginal<bf16>(h, x_u8, batch, global_batch, eps, (cudaStream_t)stream);
+    return forward_backward_marginal<float>(h, x_u8, batch, global_batch, eps, (cudaStream_t)stream);
+  }
   if (h->bf16_mode()) return forward_backward_impl<bf16>(h, x_u8, batch, global_batch, eps, gumbel_u, (cudaStream_t)stream);
   return forward_backward_impl<float>(h, x_u8, batch, global_batch, eps, gumbel_u, (cudaStream_t)stream);
 }

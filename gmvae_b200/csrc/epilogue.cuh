@@ -415,7 +415,7 @@ struct EpiBCE {
   const uint8_t* x; int64_t ldx;
   int x_row_div;            // x row = m / x_row_div (objective M: K consecutive rows share one image)
   const float* row_weight;  // [M] q(y=k|x) weights (objective M) or null -> 1
-  float* row_sum;           // [M] per-row log-likelihood (objective M) or null
+  double* row_sum;          // [M] per-row log-likelihood (objective M; double: |rec| ~ 550, its differences ~ 1) or null
   float* nll_acc;           // scalar accumulator: += -inv_bg * sum(w * loglik)
   float inv_bg;             // 1 / global batch
   float partial;
@@ -479,7 +479,7 @@ struct EpiBCE {
       d[i] = ok ? (sg - p.x[i]) * wscale : 0.f;
     }
     if (valid) {
-      if (row_sum) atomicAdd(row_sum + m, ll);
+      if (row_sum) atomicAdd(row_sum + m, (double)ll);
       partial += p.w * ll;
     }
     if constexpr (staged_io<OutT, NV>::value) {

@@ -100,8 +100,8 @@ __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float*
       l[i] = -INFINITY; a[i] = -INFINITY;
       if (k < K) {
         l[i] = logits[(int64_t)row * K + k];
-        float uu = u[(int64_t)row * K + k];
-        a[i] = (l[i] - logf(-logf(uu))) * inv_T;
+        // objective M passes u == null: y := softmax(logits) = q(y|x) itself
+        a[i] = u ? (l[i] - logf(-logf(u[(int64_t)row * K + k]))) * inv_T : l[i];
       }
       ml = fmaxf(ml, l[i]); ma = fmaxf(ma, a[i]);
     }
@@ -399,6 +399,243 @@ __global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __res
   }
   float s = block_sum(neg_logp, scratch);
   if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+}
+
+
+// ======================================================================================
+// Objective "marginal" (north_star): the reference's own blocks evaluated
+// at y = e_k for every component k, weighted by pi = q(y|x), analytic Gaussian KL.  Rows of the
+// per-component tensors are r = b*K + k.
+// ======================================================================================
+
+// prior_gmm(e_k) = rows of Wp + bp (the reference evaluates prior_gmm at one-hot y, gmvae.py:170-173)
+__global__ void prior_table_kernel(const float* __restrict__ Wp, const float* __restrict__ bp, int K, int Z2, float* __restrict__ tab) {
+  griddep_wait();
+  griddep_launch();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * Z2) tab[i] = Wp[i] + bp[i % Z2];
+}
+
+// h1[b,k,:] = relu(xproj[b,:] + W1[D+k,:] + b1): the x-projection of encoder_gmm layer 0 is computed
+// once per sample and broadcast over the K one-hot components.
+template <typename ActT>
+__global__ void expand_h1_kernel(const float* __restrict__ xproj, int64_t ldx, const float* __restrict__ Wy, const float* __restrict__ b1,
+                                 int rows, int K, int H, ActT* __restrict__ out, int64_t ldo) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t total = (int64_t)rows * (H / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (H / 4)), n = (int)(i % (H / 4)) * 4;
+    const int b = r / K, k = r % K;
+    const float4 xp = *reinterpret_cast<const float4*>(xproj + (int64_t)b * ldx + n);
+    const float4 wy = *reinterpret_cast<const float4*>(Wy + (int64_t)k * H + n);
+    const float4 bb = *reinterpret_cast<const float4*>(b1 + n);
+    float v[4] = {fmaxf(xp.x + wy.x + bb.x, 0.f), fmaxf(xp.y + wy.y + bb.y, 0.f), fmaxf(xp.z + wy.z + bb.z, 0.f),
+                  fmaxf(xp.w + wy.w + bb.w, 0.f)};
+    store_frag<4>(out + (int64_t)r * ldo + n, v, 4);
+  }
+}
+
+// One warp per row r = (b,k): z = mu_q + sigma_q eps;  KL_k = sum_j [log(s_p/s_q) + (s_q^2 + (mu_q-mu_p)^2)/(2 s_p^2) - 1/2];
+// kl accumulator += pi[b,k] KL_k / B;  klrow[r] = KL_k (needed for d loss / d pi).
+template <typename ActT>
+__global__ void head_z_m_fwd_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps, const float* __restrict__ tab,
+                                    const float* __restrict__ pi, int row0, int rows, int K, int Z, float c, float sigma_min,
+                                    float inv_bg, ActT* __restrict__ z_act, int ld_z, float* __restrict__ klrow, float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float part = 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int k = (row0 + r) % K;
+    float kl = 0.f;
+    for (int j = lane; j < Z; j += 32) {
+      float mu = enc_out[(int64_t)r * 2 * Z + j], raw = enc_out[(int64_t)r * 2 * Z + Z + j];
+      float sq = fmaxf(softplus_f(raw + c), sigma_min);
+      float mp = tab[k * 2 * Z + j], sp = fmaxf(softplus_f(tab[k * 2 * Z + Z + j] + c), sigma_min);
+      float e = eps[(int64_t)(row0 + r) * Z + j];
+      z_act[(int64_t)r * ld_z + j] = from_f32<ActT>(fmaf(sq, e, mu));
+      float d = mu - mp;
+      kl += logf(sp / sq) + (sq * sq + d * d) / (2.f * sp * sp) - 0.5f;
+    }
+    kl = warp_sum(kl);
+    if (lane == 0) { klrow[row0 + r] = kl; part += pi[row0 + r] * kl; }
+  }
+  float s = block_sum(part, scratch);
+  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+}
+
+// Backward of the z head for objective M.  Thread <-> latent dimension j, row lanes stride over the
+// chunk (same layout as head_z_bwd_cs_kernel): d_enc_out, the bias gradient of the last encoder_gmm
+// layer, and the gradient w.r.t. the prior table (accumulated per component in shared memory).
+template <typename ActT>
+__global__ void head_z_m_bwd_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps, const float* __restrict__ tab,
+                                    const float* __restrict__ pi, const float* __restrict__ dz_dec, int row0, int rows, int K, int Z,
+                                    float c, float sigma_min, float inv_bg, ActT* __restrict__ d_enc_out, int ld_out,
+                                    float* __restrict__ db_enc, float* __restrict__ dtab) {
+  griddep_wait();
+  griddep_launch();
+  extern __shared__ float sm[];                        // [2][blockDim.x] column sums, then [K][2Z] table gradient
+  const int n = blockDim.x;
+  float* dt = sm + 2 * n;
+  for (int i = threadIdx.x; i < K * 2 * Z; i += n) dt[i] = 0.f;
+  __syncthreads();
+  const int lanes = n / Z;
+  const int j = threadIdx.x % Z, rl = threadIdx.x / Z;
+  float s_mu = 0.f, s_raw = 0.f;
+  if (rl < lanes) {
+    for (int r = blockIdx.x * lanes + rl; r < rows; r += gridDim.x * lanes) {
+      const int k = (row0 + r) % K;
+      float mu = enc_out[(int64_t)r * 2 * Z + j], raw = enc_out[(int64_t)r * 2 * Z + Z + j];
+      float spq = softplus_f(raw + c), sq = fmaxf(spq, sigma_min);
+      float mp = tab[k * 2 * Z + j], rp = tab[k * 2 * Z + Z + j];
+      float spp = softplus_f(rp + c), sp = fmaxf(spp, sigma_min);
+      float e = eps[(int64_t)(row0 + r) * Z + j];
+      float w = pi[row0 + r] * inv_bg;
+      float dz = dz_dec[(int64_t)r * Z + j];
+      float d = mu - mp, isp2 = 1.f / (sp * sp);
+      float dmu = dz + w * d * isp2;
+      float dsq = dz * e + w * (sq * isp2 - 1.f / sq);
+      ActT g0 = from_f32<ActT>(dmu), g1 = from_f32<ActT>(spq >= sigma_min ? dsq * sigmoid_f(raw + c) : 0.f);
+      d_enc_out[(int64_t)r * ld_out + j] = g0; d_enc_out[(int64_t)r * ld_out + Z + j] = g1;
+      s_mu += to_f32<ActT>(g0); s_raw += to_f32<ActT>(g1);
+      float dsp = w * (1.f / sp - (sq * sq + d * d) * isp2 / sp);
+      atomicAdd(dt + k * 2 * Z + j, -w * d * isp2);
+      atomicAdd(dt + k * 2 * Z + Z + j, spp >= sigma_min ? dsp * sigmoid_f(rp + c) : 0.f);
+    }
+  }
+  sm[threadIdx.x] = s_mu; sm[n + threadIdx.x] = s_raw;
+  __syncthreads();
+  if (threadIdx.x < Z) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) { t0 += sm[l * Z + j]; t1 += sm[n + l * Z + j]; }
+    if (t0 != 0.f) atomicAdd(db_enc + j, t0);
+    if (t1 != 0.f) atomicAdd(db_enc + Z + j, t1);
+  }
+  for (int i = threadIdx.x; i < K * 2 * Z; i += n)
+    if (dt[i] != 0.f) atomicAdd(dtab + i, dt[i]);
+}
+
+// tab[k,:] = Wp[k,:] + bp  =>  dWp[k,:] += dtab[k,:],  dbp += sum_k dtab[k,:]
+__global__ void prior_table_bwd_kernel(const float* __restrict__ dtab, int K, int Z2, float* __restrict__ dWp, float* __restrict__ dbp) {
+  griddep_wait();
+  griddep_launch();
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Z2) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) { float v = dtab[k * Z2 + j]; dWp[k * Z2 + j] += v; s += v; }
+    dbp[j] += s;
+  }
+}
+
+// dxproj[b,:] = sum_k dh1[b,k,:]  (ActT, the dY of the x-part weight gradient); dWy[k,:] += sum_b dh1[b,k,:];
+// db1 += sum_{b,k} dh1.  A block owns 64 columns and a range of samples; each of its 4 row lanes
+// accumulates the per-component sums in a private shared-memory slice (no atomics in the loop).
+template <typename ActT>
+__global__ void reduce_k_kernel(const ActT* __restrict__ dh1, int64_t ldh, int b0, int nb, int K, int H, ActT* __restrict__ dxproj,
+                                int64_t ldx, float* __restrict__ dWy, float* __restrict__ db1, int samples_per_block) {
+  griddep_wait();
+  griddep_launch();
+  extern __shared__ float sm[];                        // [nty][K][64]
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6, nty = blockDim.x >> 6;
+  const int n = blockIdx.x * 64 + tx;
+  float* mine = sm + (size_t)ty * K * 64 + tx;
+  for (int k = 0; k < K; ++k) mine[k * 64] = 0.f;
+  const int s0 = blockIdx.y * samples_per_block, s1 = min(nb, s0 + samples_per_block);
+  if (n < H) {
+    for (int s = s0 + ty; s < s1; s += nty) {
+      const ActT* src = dh1 + (int64_t)s * K * ldh + n;
+      float tot = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        float v = to_f32<ActT>(src[(int64_t)k * ldh]);
+        tot += v;
+        mine[k * 64] += v;
+      }
+      dxproj[(int64_t)(b0 + s) * ldx + n] = from_f32<ActT>(tot);
+    }
+  }
+  __syncthreads();
+  if (n < H) {
+    float t = 0.f;
+    for (int k = ty; k < K; k += nty) {
+      float v = 0.f;
+      for (int l = 0; l < nty; ++l) v += sm[((size_t)l * K + k) * 64 + tx];
+      if (v != 0.f) atomicAdd(dWy + (int64_t)k * H + n, v);
+      t += v;
+    }
+    if (t != 0.f) atomicAdd(db1 + n, t);
+  }
+}
+
+// d loss / d logits_y for objective M: loss_y = sum_k pi_k c_k + sum_k pi_k log pi_k with
+// c_k = KL_k - rec_k;  dl_j = pi_j (c_j - sum_k pi_k c_k)/B + pi_j (log pi_j - sum pi log pi)/B.
+template <typename ActT>
+__global__ void head_y_m_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ pi, const double* __restrict__ rec,
+                                    const float* __restrict__ klrow, int B, int K, float inv_bg, ActT* __restrict__ dlogits, int ld_out,
+                                    float* __restrict__ db) {
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float cs[HEAD_MAXK / 32];
+#pragma unroll
+  for (int i = 0; i < HEAD_MAXK / 32; ++i) cs[i] = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+    float p[HEAD_MAXK / 32], cc[HEAD_MAXK / 32], l[HEAD_MAXK / 32];
+    double cd[HEAD_MAXK / 32];
+    float ml = -INFINITY;
+    double pcd = 0.0;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      p[i] = 0.f; cd[i] = 0.0; l[i] = -INFINITY;
+      if (k < K) {
+        l[i] = logits[(int64_t)row * K + k];
+        p[i] = pi[(int64_t)row * K + k];
+        cd[i] = (double)klrow[(int64_t)row * K + k] - rec[(int64_t)row * K + k];
+      }
+      ml = fmaxf(ml, l[i]);
+      pcd += (double)p[i] * cd[i];
+    }
+    // c_j - sum_k pi_k c_k cancels the common ~ -rec magnitude: done in double
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pcd += __shfl_xor_sync(0xffffffffu, pcd, o);
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) cc[i] = (float)(cd[i] - pcd);
+    const float pc = 0.f;
+    ml = warp_max(ml);
+    float sl = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i)
+      if (lane + 32 * i < K) sl += expf(l[i] - ml);
+    sl = warp_sum(sl);
+    const float lse = ml + logf(sl);
+    float plogp = 0.f;
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i)
+      if (lane + 32 * i < K) { float lp = l[i] - lse; plogp += expf(lp) * lp; }
+    plogp = warp_sum(plogp);
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) {
+        float lp = l[i] - lse;
+        ActT o = from_f32<ActT>((p[i] * (cc[i] - pc) + expf(lp) * (lp - plogp)) * inv_bg);
+        dlogits[(int64_t)row * ld_out + k] = o;
+        cs[i] += to_f32<ActT>(o);
+      } else if (k < ld_out) {
+        dlogits[(int64_t)row * ld_out + k] = from_f32<ActT>(0.f);
+      }
+    }
+  }
+  if (db) {
+#pragma unroll
+    for (int i = 0; i < HEAD_MAXK / 32; ++i) {
+      int k = lane + 32 * i;
+      if (k < K && cs[i] != 0.f) atomicAdd(db + k, cs[i]);
+    }
+  }
 }
 
 // ---- bias gradients: db[n] += sum_m dY[m,n] -----------------------------------------------------

@@ -225,12 +225,24 @@ def loss_terms(spec: Spec, params: Dict[str, torch.Tensor], x: torch.Tensor,
         # the reference's own blocks evaluated at y = e_k for every k,
         # weighted by q(y|x), with the analytic Gaussian KL.  eps has shape [B, K, Z].
         eye = torch.eye(K, dtype=dt)
-        mu_p, sg_p = normal_params(spec, mlp(params, "prior_gmm", eye, 1))            # [K,Z]
+        mu_p, sg_p = normal_params(spec, mlp(params, "prior_gmm", eye, 1))            # [K,Z]  (exact: a table)
         xk = x[:, None, :].expand(B, K, x.shape[1]).reshape(B * K, -1)
-        yk = eye[None].expand(B, K, K).reshape(B * K, K)
-        mu_q, sg_q = normal_params(spec, mlp(params, "encoder_gmm", torch.cat([xk, yk], 1), L))
+        # encoder_gmm([x, e_k]): layer 0 written as x W[:D] + W[D+k] + b (identical to the concat form,
+        # base.py:66) so that the rounding model can mirror the CUDA path: the x-projection uses the
+        # GEMM weight operand, the one-hot row and the bias are added in full precision.
+        D = x.shape[1]
+        w0n = "encoder_gmm_fcnet/linear_0/w"
+        w0, b0 = params[w0n], params["encoder_gmm_fcnet/linear_0/b"]
+        xproj = q.grad(x @ q.weight(w0n, w0)[:D])                                   # [B, H0], once per sample
+        h = q.act(torch.relu(xproj[:, None, :] + w0[D:][None, :, :] + b0)).reshape(B * K, -1)
+        for i in range(1, L):
+            wn = f"encoder_gmm_fcnet/linear_{i}/w"
+            h = h @ q.weight(wn, params[wn]) + params[f"encoder_gmm_fcnet/linear_{i}/b"]
+            if i != L - 1:
+                h = q.act(torch.relu(h))
+        mu_q, sg_q = normal_params(spec, q.grad(h))
         z = mu_q + sg_q * eps.to(dt).reshape(B * K, Z)
-        logits = mlp(params, "decoder", z, L) + spec.gen_bias_init
+        logits = q.grad(mlp(params, "decoder", q.fwd(z), L, q)) + spec.gen_bias_init
         rec = bernoulli_log_prob(xk, logits).reshape(B, K)
         mu_q = mu_q.reshape(B, K, Z); sg_q = sg_q.reshape(B, K, Z)
         klk = (torch.log(sg_p[None] / sg_q) + (sg_q ** 2 + (mu_q - mu_p[None]) ** 2) / (2 * sg_p[None] ** 2) - 0.5).sum(-1)

@@ -24,11 +24,11 @@ def make_spec(cfg):
                   hidden_sizes=list(cfg["hidden_sizes"]), mixture_components=cfg["mixture_components"])
 
 
-def make_engine(cfg, precision, max_batch=None, **kw):
+def make_engine(cfg, precision, max_batch=None, objective="reference", **kw):
     import gmvae_b200
     return gmvae_b200.Engine(model=cfg["model"], data_size=cfg.get("data_size", 784), latent_size=cfg["latent_size"],
                              hidden_sizes=cfg["hidden_sizes"], mixture_components=cfg["mixture_components"],
-                             precision=precision, max_batch=max_batch or cfg["batch"], init=False, **kw)
+                             precision=precision, objective=objective, max_batch=max_batch or cfg["batch"], init=False, **kw)
 
 
 def perturbed_params(spec, seed=2024, bias_scale=0.05):
@@ -55,14 +55,14 @@ def grad_errors(engine, grads_ref):
     return out
 
 
-def run_parity(cfg, precision, seed=2024, rounding_model=None):
+def run_parity(cfg, precision, seed=2024, rounding_model=None, objective="reference"):
     """Returns (loss-term errors, per-tensor gradient errors) of the CUDA step against the oracle.
     With `rounding_model` the oracle restates the bf16 storage points of the CUDA path."""
     spec = make_spec(cfg)
     params = perturbed_params(spec, seed)
-    x, labels, eps, u = O.synthetic_batch(spec, cfg["batch"])
-    terms_ref, grads_ref = O.loss_and_grads(spec, params, x, eps, u, q=rounding_model or O.EXACT)
-    eng = make_engine(cfg, precision)
+    x, labels, eps, u = O.synthetic_batch(spec, cfg["batch"], objective=objective)
+    terms_ref, grads_ref = O.loss_and_grads(spec, params, x, eps, u, objective=objective, q=rounding_model or O.EXACT)
+    eng = make_engine(cfg, precision, objective=objective)
     eng.set_parameters(params)
     loss = eng.forward_backward(x, eps=eps, gumbel_u=u)
     torch.cuda.synchronize()

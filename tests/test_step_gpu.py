@@ -48,6 +48,54 @@ def test_parity_bf16(name):
         assert v < 3 * TOL["bf16"], (name, "vs bf16 rounding model", k, v)
 
 
+MARGINAL_CASES = ["tiny_gmvae", "cfg3", "run_train_sh"]
+
+
+@pytest.mark.parametrize("chunk_rows", [0, 96])
+@pytest.mark.parametrize("name", MARGINAL_CASES)
+def test_parity_marginal_fp32(name, chunk_rows, monkeypatch):
+    """Objective M (q(y|x)-weighted per-component ELBO, analytic KL; BASELINE.json configs[2]) in the fp32
+    validation mode, whole batch at once and in chunks of per-component rows (96 rows per chunk)."""
+    if chunk_rows:
+        monkeypatch.setenv("GMVAE_M_CHUNK_ROWS", str(chunk_rows))
+    terr, gerr = run_parity(CONFIGS[name], "fp32", objective="marginal")
+    for k, v in {**terr, **gerr}.items():
+        assert v < TOL["fp32"], (name, k, v)
+
+
+@pytest.mark.parametrize("name", MARGINAL_CASES)
+def test_parity_marginal_bf16(name, monkeypatch):
+    monkeypatch.setenv("GMVAE_M_CHUNK_ROWS", "512")
+    terr, gerr = run_parity(CONFIGS[name], "bf16", objective="marginal")
+    for k, v in terr.items():
+        assert v < TOL["bf16"], (name, k, v)
+    assert max(gerr.values()) < 0.1, (name, gerr)
+    _, gerr_model = run_parity(CONFIGS[name], "bf16", rounding_model=Bf16Model(True), objective="marginal")
+    flat = sum(v * v for v in gerr_model.values()) ** 0.5 / len(gerr_model) ** 0.5
+    assert flat < 1.5 * TOL["bf16"], (name, "rms over tensors vs bf16 rounding model", flat)
+    for k, v in gerr_model.items():
+        assert v < 3 * TOL["bf16"], (name, "vs bf16 rounding model", k, v)
+
+
+def test_marginal_training_steps():
+    """A few Adam steps of objective M against the oracle trajectory (fp32 mode)."""
+    cfg = CONFIGS["tiny_gmvae"]
+    spec = make_spec(cfg)
+    params = perturbed_params(spec)
+    eng = make_engine(cfg, "fp32", objective="marginal", learning_rate=1e-3)
+    eng.set_parameters(params)
+    st = O.adam_init(params)
+    for step in range(3):
+        x, _, eps, u = O.synthetic_batch(spec, cfg["batch"], seed_data=100 + step, seed_noise=200 + step, objective="marginal")
+        terms, _ = O.train_step(spec, params, st, x, eps, u, objective="marginal", lr=1e-3)
+        loss = eng.train_step(x, eps=eps)
+        assert rel(loss[0].item(), terms["loss"].item()) < 1e-5, step
+    for n, v in eng.parameters().items():
+        r = params[n]
+        assert ((v.cpu().double().reshape(r.shape) - r).norm() / r.norm().clamp_min(1e-30)).item() < 2e-5, n
+    eng.close()
+
+
 def test_kat_zero_weights():
     """KAT-1: all-zero weights -> nll = 784 ln 2, kl = 0, nent = -ln K."""
     cfg = CONFIGS["cfg3"]
