@@ -53,6 +53,30 @@ class _EngineBacked:
         loss = eng.forward_backward(images, eps=eps, gumbel_u=gumbel_u)
         return loss[0]
 
+    # ---- inference helpers shared by VAE and GMVAE -----------------------------------------------
+    def _noise_gen(self):
+        g = getattr(self, "_gen", None)
+        if g is None:
+            g = torch.Generator(device="cpu")
+            g.manual_seed(self.random_seed if self.random_seed is not None else torch.seed() % (2 ** 31))
+            self._gen = g
+        return g
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, generator=self._noise_gen())
+
+    def reconstruct_images(self, images):
+        """Bernoulli means of p(x|z) with z ~ q(z|x[,y]) (gmvae.py:109-121, vae.py:80-88)."""
+        eng = self.engine(images.shape[0])
+        _, _, z = eng.encode(images)
+        return eng.decode(z)
+
+    def generate_sample_images(self, z=None, num_samples=1, name="sample_images"):
+        """Bernoulli means for given latent points, or for prior samples (gmvae.py:124-137, vae.py:91-102)."""
+        if z is None:
+            z = self.generate_samples(num_samples)
+        return self.engine().decode(z)
+
     # scalar summaries of the reference (`nll_scalar`, `kl_div_z`, `nent`, `elbo`)
     def summaries(self) -> dict:
         t = self.engine().loss_buf.detach().cpu()

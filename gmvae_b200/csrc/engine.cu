@@ -285,7 +285,7 @@ static int plan(gmvae_handle* h) {
     plan_shadows(h, h->decoder); plan_shadows(h, h->encoder);
     if (c.model == GMVAE_MODEL_GMVAE) { plan_shadows(h, h->encoder_y); plan_shadows(h, h->prior_gmm); }
   }
-  plan_buf(h, "dbg.a", 16); plan_buf(h, "dbg.b", 16);  // placeholders
+  plan_buf(h, "infer.acc", ACC_SLOTS * 4);
   return 0;
 }
 
@@ -530,27 +530,24 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
 }
 
 // ============================================================================ the step
+// Input conversion, noise and the encoder side of the forward pass (q(y|x), the relaxed sample y,
+// p(z|y), q(z|x,y) / q(z|x)) up to the encoder's [mu|raw] output.  Shared by the training step and by
+// gmvae_encode (reconstruct_images / transform of the model classes).
 template <typename A>
-static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
-                                 const float* u_in, cudaStream_t st) {
+static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float inv_bg, const float*& eps, const float*& u, float* acc,
+                           cudaStream_t st) {
   const gmvae_config& c = h->cfg;
   const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
-  const int Dp = ldp(D), Zp = ldp(Z), Z2p = ldp(2 * Z), Kp = ldp(K);
-  const float inv_bg = 1.f / (float)Bg;
+  const int Dp = ldp(D), Kp = ldp(K);
   const bool gm = c.model == GMVAE_MODEL_GMVAE;
-  float* acc = h->grads + h->n_params;
-  if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
-  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
-  h->reduced_upto = 0;
-
   A* x_act = h->buf<A>("x_act");
   {
     const int64_t n = (int64_t)B * D;
     // first kernel of the step: follows a memset node, launched with a full dependency
     if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
-    else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp)); GM_LAUNCHED(h, st, PC_MISC);
+    else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp));
+    GM_LAUNCHED(h, st, PC_MISC);
   }
-  const float* eps = eps_in; const float* u = u_in;
   if (!eps || (gm && !u)) {
     float* e = h->buf<float>("eps"); float* uu = gm ? h->buf<float>("u") : nullptr;
     int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
@@ -561,23 +558,15 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     if (!eps) eps = e;
     if (gm && !u) u = uu;
   }
-
-  MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder), enc = mlp_bufs<A>(h, h->encoder);
+  MlpBufs<A> enc = mlp_bufs<A>(h, h->encoder);
   float* enc_out = h->buf<float>("enc_out");
-  A* d_enc_out = h->buf<A>("d_enc_out");
-  A* z_act = h->buf<A>("z_act");
-  float* dz = h->buf<float>("dz");
-  A* dlogits_x = h->buf<A>("dec.dlogits");
   const Linear& enc_l0 = h->encoder.layers[0];
   const Linear& enc_last = h->encoder.layers[nl - 1];
   auto hid_ld = [&](int i) { return (int64_t)ldp(h->hidden[i]); };
-
-  // -------------------------------------------------------------------------- forward
-  MlpBufs<A> ey; float *logits_y = nullptr, *y_f32 = nullptr, *prior_out = nullptr; A* y_act = nullptr;
   if (gm) {
-    ey = mlp_bufs<A>(h, h->encoder_y);
-    logits_y = h->buf<float>("logits_y"); y_f32 = h->buf<float>("y_f32"); y_act = h->buf<A>("y_act");
-    prior_out = h->buf<float>("prior_out");
+    MlpBufs<A> ey = mlp_bufs<A>(h, h->encoder_y);
+    float* logits_y = h->buf<float>("logits_y"); float* y_f32 = h->buf<float>("y_f32"); A* y_act = h->buf<A>("y_act");
+    float* prior_out = h->buf<float>("prior_out");
     // q(y|x): encoder_y MLP, logits in fp32 (gmvae.py:238)
     GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, Dp, D, B, 0, st));
     {
@@ -586,7 +575,8 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
     GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, u, B, K,
-                           1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc)); GM_LAUNCHED(h, st, PC_HEADS);
+                           1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc));
+    GM_LAUNCHED(h, st, PC_HEADS);
     // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
     {
       const Linear& l = h->prior_gmm.layers[0];
@@ -625,6 +615,41 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     EpiStore<float> epi{enc_out, (int64_t)2 * Z, h->params + enc_last.b_off, nullptr, 0, 0, 1.f};
     GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : enc.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, enc_last, 0, nl == 1 ? D : -1),
                       epi, st));
+  }
+  return 0;
+}
+
+template <typename A>
+static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
+                                 const float* u_in, cudaStream_t st) {
+  const gmvae_config& c = h->cfg;
+  const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
+  const int Dp = ldp(D), Zp = ldp(Z), Z2p = ldp(2 * Z), Kp = ldp(K);
+  const float inv_bg = 1.f / (float)Bg;
+  const bool gm = c.model == GMVAE_MODEL_GMVAE;
+  float* acc = h->grads + h->n_params;
+  if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
+  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  h->reduced_upto = 0;
+
+  const float* eps = eps_in; const float* u = u_in;
+  GM_TRY(forward_encoder<A>(h, x_u8, B, inv_bg, eps, u, acc, st));
+
+  A* x_act = h->buf<A>("x_act");
+  MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder), enc = mlp_bufs<A>(h, h->encoder);
+  float* enc_out = h->buf<float>("enc_out");
+  A* d_enc_out = h->buf<A>("d_enc_out");
+  A* z_act = h->buf<A>("z_act");
+  float* dz = h->buf<float>("dz");
+  A* dlogits_x = h->buf<A>("dec.dlogits");
+  const Linear& enc_l0 = h->encoder.layers[0];
+  const Linear& enc_last = h->encoder.layers[nl - 1];
+  auto hid_ld = [&](int i) { return (int64_t)ldp(h->hidden[i]); };
+  MlpBufs<A> ey; float *logits_y = nullptr, *y_f32 = nullptr, *prior_out = nullptr; A* y_act = nullptr;
+  if (gm) {
+    ey = mlp_bufs<A>(h, h->encoder_y);
+    logits_y = h->buf<float>("logits_y"); y_f32 = h->buf<float>("y_f32"); y_act = h->buf<A>("y_act");
+    prior_out = h->buf<float>("prior_out");
   }
   // z head
   const int prior_mode = gm ? 2 : (c.model == GMVAE_MODEL_VAE_GMP ? 1 : 0);
@@ -1128,17 +1153,69 @@ int gmvae_step_graph_launch(gmvae_handle* h, void* stream) {
   return 0;
 }
 
-int gmvae_encode(gmvae_handle*, const uint8_t*, int, const float*, const float*, float*, float*, float*, void*) {
-  set_error("gmvae_encode: not built yet");
-  return -6;
+}  // extern "C"
+
+template <typename A>
+static int encode_impl(gmvae_handle* h, const uint8_t* x_u8, int B, const float* eps, const float* u, float* logits_y_out, float* z_mean,
+                       float* z_sample, cudaStream_t st) {
+  const int Z = h->Z, K = h->K;
+  float* acc = h->buf<float>("infer.acc");
+  GM_CHECK_CUDA(cudaMemsetAsync(acc, 0, ACC_SLOTS * 4, st));
+  GM_TRY(forward_encoder<A>(h, x_u8, B, 1.f / (float)B, eps, u, acc, st));
+  if (logits_y_out && h->cfg.model == GMVAE_MODEL_GMVAE)
+    GM_CHECK_CUDA(cudaMemcpyAsync(logits_y_out, h->buf<float>("logits_y"), (size_t)B * K * 4, cudaMemcpyDeviceToDevice, st));
+  const int64_t n = (int64_t)B * Z;
+  GM_CHECK_CUDA(launch_k(encode_out_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, (const float*)h->buf<float>("enc_out"), eps, B, Z,
+                         h->cfg.raw_sigma_bias, h->cfg.sigma_min, z_mean, z_sample));
+  GM_LAUNCHED(h, st, PC_HEADS);
+  return 0;
 }
-int gmvae_decode(gmvae_handle*, const float*, int, float*, void*) {
-  set_error("gmvae_decode: not built yet");
-  return -6;
+
+template <typename A>
+static int decode_impl(gmvae_handle* h, const float* z, int n, float* x_mean, cudaStream_t st) {
+  const int D = h->D, Z = h->Z, nl = h->L, Zp = ldp(Z);
+  A* z_act = h->buf<A>("z_act");
+  MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder);
+  const int64_t cnt = (int64_t)n * Z;
+  GM_CHECK_CUDA(launch_k(to_act_kernel<A>, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, false, z, n, Z, z_act, Zp));
+  GM_LAUNCHED(h, st, PC_MISC);
+  GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Zp, Z, n, 0, st));
+  const Linear& l = h->decoder.layers[nl - 1];
+  // Bernoulli mean = sigmoid(logits), logits = MLP(z) + gen_bias_init (base.py:135,138-146)
+  EpiStore<float> epi{x_mean, (int64_t)D, h->params + l.b_off, nullptr, 0, 2, 1.f, h->cfg.gen_bias_init};
+  GM_TRY(lin_fwd<A>(h, nl == 1 ? z_act : dec.hid[nl - 2], nl == 1 ? (int64_t)Zp : (int64_t)ldp(h->hidden[nl - 2]), n, view(h, l), epi, st));
+  return 0;
 }
-int gmvae_prior_table(gmvae_handle*, float*, float*, void*) {
-  set_error("gmvae_prior_table: not built yet");
-  return -6;
+
+extern "C" {
+
+int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, const float* eps, const float* gumbel_u, float* logits_y, float* z_mean,
+                 float* z_sample, void* stream) {
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(x_u8 && z_mean && z_sample, "null argument");
+  GM_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "batch must be in [1, max_batch]");
+  GM_REQUIRE(h->cfg.objective == GMVAE_OBJECTIVE_REFERENCE, "gmvae_encode needs a handle created with objective=reference");
+  if (h->bf16_mode()) return encode_impl<bf16>(h, x_u8, batch, eps, gumbel_u, logits_y, z_mean, z_sample, (cudaStream_t)stream);
+  return encode_impl<float>(h, x_u8, batch, eps, gumbel_u, logits_y, z_mean, z_sample, (cudaStream_t)stream);
+}
+int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* stream) {
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(z && x_mean, "null argument");
+  const int cap = h->cfg.objective == GMVAE_OBJECTIVE_MARGINAL ? h->chunk_samples * h->K : h->cfg.max_batch;
+  GM_REQUIRE(n > 0 && n <= cap, "n must be in [1, max_batch]");
+  if (h->bf16_mode()) return decode_impl<bf16>(h, z, n, x_mean, (cudaStream_t)stream);
+  return decode_impl<float>(h, z, n, x_mean, (cudaStream_t)stream);
+}
+int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream) {
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(mu && sigma, "null argument");
+  const int K = h->K, Z = h->Z;
+  const float* a = nullptr; const float* b = nullptr; int mode = 0;
+  if (h->cfg.model == GMVAE_MODEL_GMVAE) { a = h->params + h->prior_gmm.layers[0].w_off; b = h->params + h->prior_gmm.layers[0].b_off; mode = 2; }
+  else if (h->cfg.model == GMVAE_MODEL_VAE_GMP) { a = h->params + h->loc_off; b = h->params + h->raw_scale_off; mode = 1; }
+  GM_CHECK_CUDA(launch_k(prior_params_kernel, dim3((K * Z + 255) / 256), dim3(256), 0, (cudaStream_t)stream, false, a, b, mode, K, Z,
+                         h->cfg.raw_sigma_bias, h->cfg.sigma_min, mu, sigma));
+  return 0;
 }
 
 int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int64_t n_u, void* stream) {

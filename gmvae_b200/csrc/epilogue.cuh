@@ -346,8 +346,9 @@ struct EpiStore {
   const float* bias;        // [N] or null
   const float* addend;      // EPI_ADDEND: [M, ld_add] fp32 (the y-part of encoder_gmm layer 0 in fp32 mode)
   int64_t ld_add;
-  int relu;
+  int relu;                 // 0 none, 1 ReLU, 2 sigmoid (Bernoulli mean of the decoder, inference only)
   float scale;
+  float shift;              // constant added with the bias (gen_bias_init); 0 when omitted from the initialiser
 
   template <int NV> struct Pre { float b[NV >= 16 ? 1 : NV]; float a[(MODE != EPI_PLAIN) ? NV : 1]; };
 
@@ -387,7 +388,8 @@ struct EpiStore {
     for (int i = 0; i < NV; ++i) {
       if constexpr (NV >= 16) v[i] = fmaf(acc[i], scale, bb[i]); else v[i] = fmaf(acc[i], scale, p.b[i]);
       if constexpr (MODE == EPI_ADDEND) v[i] += p.a[i];
-      if (relu) v[i] = fmaxf(v[i], 0.f);
+      if (relu == 1) v[i] = fmaxf(v[i], 0.f);
+      else if (relu == 2) v[i] = sigmoid_f(v[i] + shift);
       if constexpr (MODE == EPI_ACCUM) v[i] += p.a[i];
     }
     // columns >= nvalid need no masking on the staged path: their accumulators are exactly 0 (the B

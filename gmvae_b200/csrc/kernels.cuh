@@ -338,6 +338,47 @@ __global__ void head_z_bwd_cs_kernel(const float* __restrict__ enc_out, const fl
   }
 }
 
+// ---- inference helpers (gmvae.py:109-188, vae.py:80-123) ------------------------------------------
+// z_mean = mu, z_sample = mu + sigma eps from the encoder's [mu|raw] output
+__global__ void encode_out_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps, int B, int Z, float c, float sigma_min,
+                                  float* __restrict__ z_mean, float* __restrict__ z_sample) {
+  griddep_wait();
+  griddep_launch();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)B * Z) {
+    int b = (int)(i / Z), j = (int)(i % Z);
+    float mu = enc_out[(int64_t)b * 2 * Z + j];
+    float sg = fmaxf(softplus_f(enc_out[(int64_t)b * 2 * Z + Z + j] + c), sigma_min);
+    z_mean[i] = mu;
+    z_sample[i] = fmaf(sg, eps[i], mu);
+  }
+}
+template <typename T>
+__global__ void to_act_kernel(const float* __restrict__ in, int rows, int cols, T* __restrict__ out, int ld) {
+  griddep_wait();
+  griddep_launch();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)rows * cols) out[(i / cols) * ld + i % cols] = from_f32<T>(in[i]);
+}
+// mode 2: GMVAE prior_gmm(one_hot(k)) = (Wp[k,:Z] + bp[:Z], softplus(Wp[k,Z:] + bp[Z:] + c));
+// mode 1: VAE_GMP components (loc, softplus(raw_scale_diag)); mode 0: standard normal.
+__global__ void prior_params_kernel(const float* __restrict__ a, const float* __restrict__ b, int mode, int K, int Z, float c,
+                                    float sigma_min, float* __restrict__ mu, float* __restrict__ sigma) {
+  griddep_wait();
+  griddep_launch();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * Z) return;
+  int k = i / Z, j = i % Z;
+  if (mode == 2) {
+    mu[i] = a[k * 2 * Z + j] + b[j];
+    sigma[i] = fmaxf(softplus_f(a[k * 2 * Z + Z + j] + b[Z + j] + c), sigma_min);
+  } else if (mode == 1) {
+    mu[i] = a[i]; sigma[i] = softplus_f(b[i]);
+  } else {
+    mu[i] = 0.f; sigma[i] = 1.f;
+  }
+}
+
 // ---- VAE_GMP mixture prior (vae.py:231-244, 181): forward value and every gradient -------------
 // log p(z) = logsumexp_k [ log_softmax(m)_k + log N(z; loc_k, softplus(raw_scale_k)) ]
 // One warp per row; lanes stride over Z.  Adds -log p / B to the KL accumulator, writes

@@ -186,6 +186,42 @@ class Engine:
                                              self._stream()), "gmvae_train_step")
         return self.loss_buf
 
+    # ------------------------------------------------------------------ forward-only helpers
+    def encode(self, x, eps=None, gumbel_u=None):
+        """(logits_y or None, z_mean, z_sample): encoder side of the forward pass (gmvae.py:140-150, vae.py:105-112)."""
+        xu = self._as_u8(x)
+        B = xu.shape[0]
+        Z, K = self.latent_size, self.mixture_components
+        e = self._as_f32(eps, (B, Z))
+        u = self._as_f32(gumbel_u, (B, K)) if self.model == "gmvae" else None
+        logits = torch.empty(B, K, dtype=torch.float32, device=self.device) if self.model == "gmvae" else None
+        zm = torch.empty(B, Z, dtype=torch.float32, device=self.device)
+        zs = torch.empty(B, Z, dtype=torch.float32, device=self.device)
+        self._keep = [xu, e, u]
+        _lib.check(self.lib.gmvae_encode(self._h, xu.data_ptr(), B, _ptr(e), _ptr(u), _ptr(logits), zm.data_ptr(), zs.data_ptr(),
+                                         self._stream()), "gmvae_encode")
+        return logits, zm, zs
+
+    def decode(self, z) -> torch.Tensor:
+        """Bernoulli mean sigmoid(decoder(z)) [n, data_size] (base.py:138-146)."""
+        z = torch.as_tensor(z).to(self.device, torch.float32).reshape(-1, self.latent_size).contiguous()
+        out = torch.empty(z.shape[0], self.data_size, dtype=torch.float32, device=self.device)
+        for i in range(0, z.shape[0], self.max_batch):
+            zc = z[i:i + self.max_batch]
+            _lib.check(self.lib.gmvae_decode(self._h, zc.data_ptr(), zc.shape[0], out[i:i + self.max_batch].data_ptr(), self._stream()),
+                       "gmvae_decode")
+        self._keep = [z]
+        return out
+
+    def prior_table(self):
+        """(mu [K,Z], sigma [K,Z]) of the prior components: prior_gmm(one_hot(k)) for the GMVAE
+        (gmvae.py:170-173), (loc, softplus(raw_scale_diag)) for VAE_GMP, N(0,I) for the VAE."""
+        K = self.mixture_components if self.model != "vae" else 1
+        mu = torch.empty(K, self.latent_size, dtype=torch.float32, device=self.device)
+        sg = torch.empty_like(mu)
+        _lib.check(self.lib.gmvae_prior_table(self._h, mu.data_ptr(), sg.data_ptr(), self._stream()), "gmvae_prior_table")
+        return mu, sg
+
     # ------------------------------------------------------------------ CUDA graph of the whole step
     def capture_step(self, x_static: torch.Tensor, eps=None, gumbel_u=None, global_batch: Optional[int] = None):
         """Captures train_step on fixed buffers; refill `x_static` (uint8 [B, D] on this device) in

@@ -29,6 +29,29 @@ class GMVAE(_EngineBacked):
                     gen_bias_init=dec._bias_init, temperature=ey._temperature)
 
 
+    def transform(self, inputs):
+        """Latent code z ~ q(z|x,y), y ~ q(y|x) (gmvae.py:140-149; the reference samples here, it does not take the mean)."""
+        _, _, z = self.engine(inputs.shape[0]).encode(inputs)
+        return z
+
+    def encoder_y_logits(self, x):
+        """Logits of q(y|x) (what `encoder_y(x).distribution.logits` is in the reference, gmvae.py:263,271)."""
+        logits, _, _ = self.engine(x.shape[0]).encode(x)
+        return logits
+
+    def generate_samples(self, num_samples, clusters=None):
+        """Samples from the prior components p(z | y = one_hot(k)) (gmvae.py:152-188): for every k (or for
+        the given `clusters`) `num_samples` draws; shape [num_samples * n_clusters, latent_size], sample-major
+        like the reference's reshape of [num_samples, n_clusters, latent_size]."""
+        import torch
+        mu, sg = self.engine().prior_table()
+        if clusters is not None:
+            idx = torch.as_tensor(clusters, dtype=torch.long, device=mu.device)
+            mu, sg = mu[idx], sg[idx]
+        eps = self._randn(num_samples, mu.shape[0], mu.shape[1]).to(mu.device)
+        return (mu[None] + sg[None] * eps).reshape(num_samples * mu.shape[0], -1)
+
+
 class TrainableGMVAE(GMVAE):
     """gmvae.py:191-274."""
 

@@ -29,6 +29,25 @@ class VAE(_EngineBacked):
     def prior(self):
         return self._prior
 
+    def transform(self, inputs):
+        """Mean latent code q(z|x).mean (vae.py:105-112)."""
+        _, z_mean, _ = self.engine(inputs.shape[0]).encode(inputs)
+        return z_mean
+
+    def generate_samples(self, num_samples):
+        """`num_samples` draws from the prior (vae.py:115-123): N(0,I), or the learned mixture
+        (component ~ Categorical(mixture_logits), then N(loc_k, softplus(raw_scale_diag_k)))."""
+        import torch
+        eng = self.engine()
+        mu, sg = eng.prior_table()
+        Z = mu.shape[1]
+        eps = self._randn(num_samples, Z).to(mu.device)
+        if self.mix_components > 1:
+            logits = eng.parameters()["mixture_logits"].detach().cpu()
+            comp = torch.multinomial(torch.softmax(logits, 0), num_samples, replacement=True, generator=self._noise_gen()).to(mu.device)
+            return mu[comp] + sg[comp] * eps
+        return eps
+
 
 class TrainableVAE(VAE):
     """vae.py:126-188."""

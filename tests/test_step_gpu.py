@@ -219,3 +219,44 @@ def test_dropin_classes_run_model():
     lv = v.run_model(x, x, eps=eps)
     pv = {n: t.detach().cpu().double() for n, t in v.engine().parameters().items()}
     assert rel(lv.item(), O.loss_terms(make_spec(CONFIGS["cfg1"]), pv, x, eps)["loss"].item()) < 1e-5
+
+
+def test_inference_helpers_match_oracle_blocks():
+    """reconstruct_images / transform / generate_samples / generate_sample_images (gmvae.py:109-188,
+    vae.py:80-123) on the forward-only C-ABI entry points, against the oracle's blocks."""
+    import gmvae_b200
+    cfg = CONFIGS["cfg3"]
+    spec = make_spec(cfg)
+    params = perturbed_params(spec)
+    x, _, eps, u = O.synthetic_batch(spec, cfg["batch"])
+    eng = make_engine(cfg, "fp32")
+    eng.set_parameters(params)
+    logits, z_mean, z_sample = eng.encode(x, eps=eps, gumbel_u=u)
+    ref = O.loss_terms(spec, params, x, eps, u)
+    assert (logits.cpu().double() - ref["logits_y"]).abs().max() < 1e-4
+    assert (z_sample.cpu().double() - ref["z"]).abs().max() < 1e-4
+    xm = eng.decode(z_sample)
+    assert (xm.cpu().double() - torch.sigmoid(ref["logits_x"])).abs().max() < 1e-5
+    mu, sg = eng.prior_table()
+    eye = torch.eye(10, dtype=torch.float64)
+    mu_ref, sg_ref = O.normal_params(spec, O.mlp(params, "prior_gmm", eye, 1))
+    assert (mu.cpu().double() - mu_ref).abs().max() < 1e-6 and (sg.cpu().double() - sg_ref).abs().max() < 1e-6
+    eng.close()
+    # the model-class surface
+    m = gmvae_b200.create_gmvae(784, 64, mixture_components=10, fcnet_hidden_sizes=[512, 512], sigma_min=0.0, raw_sigma_bias=0.5,
+                                random_seed=7)
+    m.configure(precision="bf16", max_batch=128)
+    rec = m.reconstruct_images(x)
+    assert tuple(rec.shape) == (100, 784) and 0.0 <= rec.min().item() and rec.max().item() <= 1.0
+    assert tuple(m.transform(x).shape) == (100, 64)
+    z = m.generate_samples(3)
+    assert tuple(z.shape) == (30, 64)
+    assert tuple(m.generate_samples(2, clusters=[1, 4, 4]).shape) == (6, 64)
+    assert tuple(m.generate_sample_images(num_samples=1).shape) == (10, 784)
+    v = gmvae_b200.create_vae(784, 64, mixture_components=10, fcnet_hidden_sizes=[512, 512], sigma_min=0.0, raw_sigma_bias=0.5,
+                              random_seed=7)
+    v.configure(precision="bf16", max_batch=128)
+    assert tuple(v.transform(x).shape) == (100, 64)
+    assert tuple(v.generate_samples(10).shape) == (10, 64)
+    assert tuple(v.generate_sample_images(num_samples=10).shape) == (10, 784)
+    assert tuple(v.reconstruct_images(x).shape) == (100, 784)
