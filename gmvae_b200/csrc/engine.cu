@@ -46,6 +46,8 @@ EncodeTiledFn get_encode_fn() {
 
 long long* g_trace = nullptr;
 
+int g_reserved_sms = 0;   // SMs left to the NCCL kernels while a data-parallel step is running
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -54,7 +56,7 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return std::max(8, n - g_reserved_sms);
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
@@ -1090,6 +1092,19 @@ int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int ran
   GM_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad world_size / rank");
   ncclUniqueId uid; memcpy(&uid, id, 128);
   GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+  // The persistent GEMM kernels occupy every SM they are given (one ~210 KB CTA each), which would
+  // starve the all-reduce running on the side stream.  Under data parallelism a few SMs are left to
+  // NCCL and NCCL is told to use no more channels (= CTAs) than that.
+  if (world_size > 1) {
+    const char* env = getenv("GMVAE_COMM_SMS");
+    int reserve = env ? atoi(env) : 8;
+    tc::g_reserved_sms = std::max(0, std::min(64, reserve));
+    if (tc::g_reserved_sms > 0) {
+      std::string v = std::to_string(tc::g_reserved_sms);
+      setenv("NCCL_MAX_NCHANNELS", v.c_str(), 0);
+      setenv("NCCL_MAX_CTAS", v.c_str(), 0);
+    }
+  }
   ncclResult_t r = ncclCommInitRank(&h->comm, world_size, uid, rank);
   if (r != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); return -5; }
   h->world = world_size; h->rank = rank;

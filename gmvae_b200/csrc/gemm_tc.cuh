@@ -378,6 +378,7 @@ struct Operand {
 };
 
 int num_sms();
+extern int g_reserved_sms;
 extern long long* g_trace;   // device buffer of clock64 stamps of CTA 0 (test hook), normally null
 
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
