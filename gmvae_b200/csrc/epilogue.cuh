@@ -208,6 +208,7 @@ struct EpiCtx {
   uint8_t* patch;   // per-warp scratch (>= 2 KB) or null (CUDA-core GEMM: rows are stored directly)
   int rows_valid;   // valid rows of the warp's 32-row group (lane l <-> row m_base + l)
   const float* sbias;  // tensor-core kernel: this chunk's bias values staged in shared memory by tile_begin()
+  float* scs;          // tensor-core kernel: this chunk's slice of the CTA-wide column-sum accumulator (shared memory)
 };
 // Chunks are moved in 16-byte pieces; a ragged last chunk (N not a multiple of NV) rounds its
 // width up to 8 columns, which stays inside the zero padding of the row (strides are multiples of 8).
@@ -249,8 +250,11 @@ __device__ __forceinline__ void store_chunk_bf16(bf16* base /*row m_base, col n0
 // Column sums of the chunk just staged in the patch by store_chunk_bf16 (call with keep_patch = true
 // there, then this, which ends with the releasing __syncwarp): lanes 0..15 / 16..31 each walk 16 rows
 // of a 32-bit column pair, one shuffle merges the halves, NV/2 lanes issue two atomics each.
+// The sums go into the CTA-wide shared accumulator ctx.scs (flushed to global memory by the kernel
+// once per CTA and n-tile): per-warp global atomics would put M/32 same-address atomics on every
+// column, which L2 serialises.
 template <int NV>
-__device__ __forceinline__ void colsum_from_patch(float* dst, int n0, int nvalid, const EpiCtx& ctx) {
+__device__ __forceinline__ void colsum_from_patch(int nvalid, const EpiCtx& ctx) {
   constexpr int U = NV / 8, WORDS = NV / 2;              // 32-bit words (column pairs) per row
   const int lane = threadIdx.x & 31;
   const uint32_t patch = smem_addr(ctx.patch);
@@ -273,8 +277,9 @@ __device__ __forceinline__ void colsum_from_patch(float* dst, int n0, int nvalid
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
   }
   if (grp == 0) {
-    if (2 * w < nvalid && s0 != 0.f) atomicAdd(dst + n0 + 2 * w, s0);
-    if (2 * w + 1 < nvalid && s1 != 0.f) atomicAdd(dst + n0 + 2 * w + 1, s1);
+    const uint32_t a = smem_addr(ctx.scs) + 8 * w;
+    if (2 * w < nvalid && s0 != 0.f) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(s0) : "memory");
+    if (2 * w + 1 < nvalid && s1 != 0.f) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a + 4), "f"(s1) : "memory");
   }
   __syncwarp();
 }
@@ -354,6 +359,7 @@ struct EpiStore {
 
   template <int BN>
   __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
+  __device__ __forceinline__ float* colsum_dst() const { return nullptr; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
@@ -428,6 +434,7 @@ struct EpiBCE {
 
   template <int BN>
   __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
+  __device__ __forceinline__ float* colsum_dst() const { return colsum; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
@@ -489,7 +496,7 @@ struct EpiBCE {
       // of the values as stored, bf16-rounded) is read back from the same patch
       store_chunk_bf16<NV>(reinterpret_cast<bf16*>(dlogits) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, d, nvalid, ctx,
                            colsum != nullptr);
-      if (colsum) colsum_from_patch<NV>(colsum, n0, nvalid, ctx);
+      if (colsum) colsum_from_patch<NV>(nvalid, ctx);
     } else {
       if (valid) store_frag<NV>(dlogits + (int64_t)m * ld + n0, d, nvalid);
     }
@@ -515,6 +522,7 @@ struct EpiReluMask {
 
   template <int BN>
   __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
+  __device__ __forceinline__ float* colsum_dst() const { return colsum; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx& ctx) const {
@@ -548,7 +556,7 @@ struct EpiReluMask {
     if constexpr (staged_io<OutT, NV>::value) {
       store_chunk_bf16<NV>(reinterpret_cast<bf16*>(out) + (int64_t)(m - (int)(threadIdx.x & 31)) * ld + n0, ld, v, nvalid, ctx,
                            colsum != nullptr);
-      if (colsum) colsum_from_patch<NV>(colsum, n0, nvalid, ctx);   // bias gradient of the layer below, as stored
+      if (colsum) colsum_from_patch<NV>(nvalid, ctx);   // bias gradient of the layer below, as stored
     } else {
       if (valid) store_frag<NV>(out + (int64_t)m * ld + n0, v, nvalid);
     }
@@ -562,6 +570,7 @@ struct EpiAtomicAdd {
   template <int NV> struct Pre {};
   template <int BN>
   __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
+  __device__ __forceinline__ float* colsum_dst() const { return nullptr; }
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int, int, int, bool, const EpiCtx&) const { return Pre<NV>(); }
   template <int NV>

@@ -69,7 +69,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sAm, int64_t sAk, const TB* _
       int m = m0 + ty * 4 + i;
       if (m < M && n < N) {
         const int nv = min(4, N - n);
-        const EpiCtx ctx{nullptr, 0, nullptr};
+        const EpiCtx ctx{nullptr, 0, nullptr, nullptr};
         auto pre = epi.template prefetch<4>(m, n, nv, true, ctx);
         epi.template row<4>(m, n, acc[i], nv, true, pre, ctx);
       }

@@ -168,11 +168,11 @@ template <int BLOCK_N> __host__ __device__ constexpr int stage_bytes() { return 
 template <int BLOCK_N> __host__ __device__ constexpr int stages_for() {
   return (196 * 1024) / stage_bytes<BLOCK_N>() > 8 ? 8 : (196 * 1024) / stage_bytes<BLOCK_N>();
 }
-constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quadrant
-constexpr int PATCH_BYTES = 2048;                  // per-epilogue-warp transposition scratch (epilogue.cuh)
+constexpr int EPI_WARPS = 16;                      // four warps per TMEM lane quadrant (the epilogue is latency-bound: TLP)
+constexpr int PATCH_BYTES = 1024;                  // per-epilogue-warp transposition scratch: 32 rows x 16 bf16 (epilogue.cuh)
 template <int BLOCK_N> __host__ __device__ constexpr int smem_bytes() {
   return stages_for<BLOCK_N>() * stage_bytes<BLOCK_N>() + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * PATCH_BYTES +
-         2 * 256 * 4 /*double-buffered bias*/;
+         2 * 256 * 4 /*double-buffered bias*/ + 256 * 4 /*column-sum accumulator*/;
 }
 
 constexpr int NUM_THREADS2 = 64 + EPI_WARPS * 32;  // + TMA producer warp + MMA warp
@@ -191,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
   constexpr int STAGE_BYTES = stage_bytes<BLOCK_N>();
   constexpr int ACC_COLS = tmem_cols_for(BLOCK_N);         // column stride between the two accumulators
   constexpr int TMEM_COLS = 2 * ACC_COLS;
-  constexpr int CW = (BLOCK_N % 32 == 0) ? 32 : 16;
+  constexpr int CW = 16;                               // columns per epilogue chunk
   constexpr int NCHUNK = BLOCK_N / CW;
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
   static_assert(!B_MN || BLOCK_N % 64 == 0, "MN-major B is loaded in 64-column slabs");
@@ -208,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint8_t* patches = smem + STAGES * STAGE_BYTES + 256;
   float* sbias_all = reinterpret_cast<float*>(patches + EPI_WARPS * PATCH_BYTES);   // [2][256]
+  float* scs_all = sbias_all + 2 * 256;                                              // [256] column sums of the current n-tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
@@ -309,7 +310,20 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
     Epi epi = epi_in;
     const int e = warp - 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = e >> 2;             // the two warps of a quadrant interleave column chunks
+    const int half = e >> 2;             // the EPI_WARPS/4 warps of a quadrant interleave column chunks
+    // Fused column sums (bias gradients): accumulated per CTA in shared memory and flushed with one
+    // global atomic per column when the CTA moves to another n-tile and at the end.
+    float* const cs_dst = epi.colsum_dst();
+    const int et = (int)threadIdx.x - 64;               // index within the epilogue threads
+    int cs_n0 = -1;
+    if (cs_dst) { for (int i = et; i < 256; i += EPI_WARPS * 32) scs_all[i] = 0.f; }
+    auto cs_flush = [&]() {                               // caller guarantees all adds are done (named barrier)
+      for (int i = et; i < BLOCK_N; i += EPI_WARPS * 32) {
+        const float v = scs_all[i];
+        if (v != 0.f && cs_n0 + i < N) atomicAdd(cs_dst + cs_n0 + i, v);
+        scs_all[i] = 0.f;
+      }
+    };
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int z = t / tiles_mn, mn = t - z * tiles_mn;
@@ -320,35 +334,56 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
       float* sbias = sbias_all + (it & 1) * 256;
       epi.template tile_begin<BLOCK_N>(n0, N, sbias, (int)threadIdx.x - 64, EPI_WARPS * 32);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      EpiCtx ctx{patches + e * PATCH_BYTES, max(0, min(32, M - (m0 + quad * 32))), sbias};
+      if (cs_dst && cs_n0 != n0) {                        // uniform over the epilogue warps
+        if (cs_n0 >= 0) {
+          cs_flush();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
+        cs_n0 = n0;
+      }
+      EpiCtx ctx{patches + e * PATCH_BYTES, max(0, min(32, M - (m0 + quad * 32))), sbias, scs_all};
       const bool tr = trace && blockIdx.x == 0 && e == 0 && lane == 0;
       if (tr) trace[16 * it + 6] = clock64();
+      const bool mvalid = m < M;
+      constexpr int CSTEP = EPI_WARPS / 4;
+      auto chunk_ok = [&](int ci) { return ci < NCHUNK && n0 + ci * CW < N; };   // warp-uniform
+      // The epilogue's own global loads (ReLU mask, image bytes) run one chunk ahead: the first
+      // chunk's are issued before the accumulator is even complete, the next chunk's while the
+      // current one is processed.
+      typename Epi::template Pre<CW> pre_cur, pre_next;
+      if (chunk_ok(half)) pre_cur = epi.template prefetch<CW>(m, n0 + half * CW, min(CW, N - (n0 + half * CW)), mvalid, ctx);
       mbar_wait(&tmem_full_bar[as], ap);
       tc_fence_after();
       if (tr) trace[16 * it + 7] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * ACC_COLS);
 #pragma unroll 1
-      for (int ci = half; ci < NCHUNK; ci += 2) {
+      for (int ci = half; chunk_ok(ci); ci += CSTEP) {
         const int n = n0 + ci * CW;
-        if (n >= N) break;                               // warp-uniform
         const int nv = min(CW, N - n);
         uint32_t r[CW];
         ctx.sbias = sbias + ci * CW;
+        ctx.scs = scs_all + ci * CW;
         if constexpr (CW == 32) tmem_ld32_issue(taddr + ci * CW, r); else tmem_ld16_issue(taddr + ci * CW, r);
-        auto pre = epi.template prefetch<CW>(m, n, nv, m < M, ctx);   // global loads fly while TMEM is read
+        const int cn = ci + CSTEP;
+        if (chunk_ok(cn)) pre_next = epi.template prefetch<CW>(m, n0 + cn * CW, min(CW, N - (n0 + cn * CW)), mvalid, ctx);
         if constexpr (CW == 32) tmem_ld32_wait(r); else tmem_ld16_wait(r);
-        if (tr && ci / 2 < 3) trace[16 * it + 13 + ci / 2] = clock64();
+        if (tr && ci / CSTEP < 3) trace[16 * it + 13 + ci / CSTEP] = clock64();
         float v[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
-        epi.template row<CW>(m, n, v, nv, m < M, pre, ctx);
-        if (tr && ci / 2 < 4) trace[16 * it + 8 + ci / 2] = clock64();
+        epi.template row<CW>(m, n, v, nv, mvalid, pre_cur, ctx);
+        if (tr && ci / CSTEP < 4) trace[16 * it + 8 + ci / CSTEP] = clock64();
+        pre_cur = pre_next;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
       epi.finish_warp();
       if (tr) trace[16 * it + 12] = clock64();
+    }
+    if (cs_dst && cs_n0 >= 0) {
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      cs_flush();
     }
   }
   tc_fence_before();
