@@ -108,6 +108,21 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return r;
 }
 
+// ----------------------------------------------------------------------------- loss accumulators
+// The three un-normalised loss sums (nll, kl, nent) live in the tail of the gradient buffer so that
+// one all-reduce covers them.  Each is spread over 32 fp32 slots (slot chosen by the adding block)
+// and summed in double by the finalising kernel: thousands of same-sized addends into ONE fp32
+// accumulator round in a correlated way (measured: 1.6e-4 relative on the 16 384-sample KAT).
+enum { ACC_NLL = 0, ACC_KL = 32, ACC_NENT = 64, ACC_PER_TERM = 32, ACC_SLOTS = 96 };
+__device__ __forceinline__ void acc_add(float* acc, int term, float v) {
+  atomicAdd(acc + term + ((blockIdx.x + (threadIdx.x >> 5)) & (ACC_PER_TERM - 1)), v);
+}
+__device__ __forceinline__ float acc_total(const float* acc, int term) {
+  double s = 0.0;
+  for (int i = 0; i < ACC_PER_TERM; ++i) s += (double)acc[term + i];
+  return (float)s;
+}
+
 // ----------------------------------------------------------------------------- Philox4x32-10
 struct Philox {
   __device__ static __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {

@@ -681,7 +681,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     LinView Ld = view(h, l);
     dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, in, ldin, Ld);
     EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8, (int64_t)D, 1, nullptr, (double*)nullptr,
-                  acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
+                  acc, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
     GM_TRY(lin_fwd<A>(h, in, ldin, B, Ld, epi, st));
   }
 
@@ -847,7 +847,7 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
       LinView Ld = view(h, l);
       dec_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM) && tc_ok_fwd<A>(h, dec.hid[nl - 2], hid_ld(nl - 2), Ld);
       EpiBCE<A> epi{dlogits_x, (int64_t)Dp, h->params + l.b_off, c.gen_bias_init, x_u8 + (int64_t)b0 * D, (int64_t)D, K, pi + row0, rec + row0,
-                    acc + ACC_NLL, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
+                    acc, inv_bg, 0.f, dec_bias_fused ? h->grads + l.b_off : nullptr, h->bf16_mode() ? 1 : 0};
       GM_TRY(lin_fwd<A>(h, dec.hid[nl - 2], hid_ld(nl - 2), R, Ld, epi, st));
     }
     GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, R, st, dec_bias_fused)));
@@ -860,6 +860,12 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
       const int lanes = 256 / Z;
       const int blocks = std::max(1, std::min(2 * tc::num_sms(), (R + lanes - 1) / lanes));
       const size_t smem = (size_t)(2 * 256 + K * 2 * Z) * sizeof(float);
+      GM_REQUIRE(smem <= 200 * 1024, "objective=marginal: mixture_components * latent_size too large for the prior-table gradient tile");
+      static size_t smem_set = 0;
+      if (smem > smem_set) {
+        GM_CHECK_CUDA(cudaFuncSetAttribute(head_z_m_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+      }
       GM_CHECK_CUDA(launch_k(head_z_m_bwd_kernel<A>, dim3(blocks), dim3(256), smem, st, true, (const float*)enc_out, eps, (const float*)tab,
                              (const float*)pi, (const float*)dz, row0, R, K, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, d_enc_out, Z2p,
                              h->grads + enc_last.b_off, dtab));

@@ -424,7 +424,7 @@ struct EpiBCE {
   int x_row_div;            // x row = m / x_row_div (objective M: K consecutive rows share one image)
   const float* row_weight;  // [M] q(y=k|x) weights (objective M) or null -> 1
   double* row_sum;          // [M] per-row log-likelihood (objective M; double: |rec| ~ 550, its differences ~ 1) or null
-  float* nll_acc;           // scalar accumulator: += -inv_bg * sum(w * loglik)
+  float* nll_acc;           // base of the loss accumulators (acc_add): nll += -inv_bg * sum(w * loglik)
   float inv_bg;             // 1 / global batch
   float partial;
   float* colsum;            // fused bias gradient db[n] += sum_m dlogits[m,n] (tensor-core path only) or null
@@ -503,7 +503,7 @@ struct EpiBCE {
   }
   __device__ __forceinline__ void finish_warp() {
     float s = warp_sum(partial);
-    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(nll_acc, -inv_bg * s);
+    if ((threadIdx.x & 31) == 0 && s != 0.f) acc_add(nll_acc, ACC_NLL, -inv_bg * s);
     partial = 0.f;
   }
 };

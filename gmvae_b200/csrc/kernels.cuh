@@ -7,8 +7,6 @@
 
 namespace gmvae {
 
-// Loss accumulators live in the tail of the gradient buffer (so one all-reduce covers them).
-enum { ACC_NLL = 0, ACC_KL = 1, ACC_NENT = 2, ACC_SLOTS = 8 };
 
 struct DeviceState {           // owned by the handle, lives on the device
   long long step;              // global_step (runners.py:171)
@@ -129,7 +127,7 @@ __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float*
     }
   }
   float s = block_sum(ent, scratch);
-  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_NENT, s * inv_bg);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_NENT, s * inv_bg);
 }
 
 // ---- q(y|x) head, backward --------------------------------------------------------------------
@@ -232,7 +230,7 @@ __global__ void head_z_fwd_kernel(const float* __restrict__ enc_out, const float
     kl = logq - logp;
   }
   float s = block_sum(kl, scratch);
-  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_KL, s * inv_bg);
 }
 
 // ---- q(z|.) head, backward ---------------------------------------------------------------------
@@ -439,7 +437,7 @@ __global__ void gmp_prior_kernel(const float* __restrict__ z, const float* __res
     }
   }
   float s = block_sum(neg_logp, scratch);
-  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_KL, s * inv_bg);
 }
 
 
@@ -504,7 +502,7 @@ __global__ void head_z_m_fwd_kernel(const float* __restrict__ enc_out, const flo
     if (lane == 0) { klrow[row0 + r] = kl; part += pi[row0 + r] * kl; }
   }
   float s = block_sum(part, scratch);
-  if (threadIdx.x == 0 && s != 0.f) atomicAdd(acc + ACC_KL, s * inv_bg);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_KL, s * inv_bg);
 }
 
 // Backward of the z head for objective M.  Thread <-> latent dimension j, row lanes stride over the
@@ -720,7 +718,7 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __res
   griddep_wait();
   griddep_launch();
   if (threadIdx.x == 0) {
-    float nll = acc[ACC_NLL], kl = acc[ACC_KL], ne = acc[ACC_NENT];
+    float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
     out[0] = nll + kl + ne;  // gmvae.py:267 / vae.py:185
     out[1] = nll; out[2] = kl; out[3] = ne;
   }
@@ -736,7 +734,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   griddep_launch();
   __shared__ float lr_t_s;
   if (loss_out && blockIdx.x == 0 && threadIdx.x == 32) {   // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
-    float nll = acc[ACC_NLL], kl = acc[ACC_KL], ne = acc[ACC_NENT];
+    float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
     loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
   }
   if (threadIdx.x == 0) {

@@ -86,8 +86,8 @@ GMVAE_API int gmvae_create(const gmvae_config* cfg, gmvae_handle** out);
 GMVAE_API void gmvae_destroy(gmvae_handle* h);
 
 /* Flat layout of tf.trainable_variables() (runners.py:182). param_count includes the
- * 16-byte alignment padding between tensors; grad_count = param_count + 8 (the tail holds
- * the un-normalised loss accumulators so that one all-reduce covers both). */
+ * 16-byte alignment padding between tensors; grad_count = param_count + 96 (the tail holds
+ * the loss accumulators, 32 fp32 slots per term, so that one all-reduce covers both). */
 GMVAE_API int64_t gmvae_param_count(const gmvae_handle* h);
 GMVAE_API int64_t gmvae_grad_count(const gmvae_handle* h);
 GMVAE_API int gmvae_num_params(const gmvae_handle* h);

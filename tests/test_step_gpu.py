@@ -260,3 +260,65 @@ def test_inference_helpers_match_oracle_blocks():
     assert tuple(v.generate_samples(10).shape) == (10, 64)
     assert tuple(v.generate_sample_images(num_samples=10).shape) == (10, 784)
     assert tuple(v.reconstruct_images(x).shape) == (100, 784)
+
+
+# ---------------------------------------------------------------- BASELINE.json full-size properties
+FULL = dict(model="gmvae", latent_size=64, hidden_sizes=[512, 512], mixture_components=10, batch=16384)   # cfg4, one GPU's share
+
+
+def _full_inputs(B):
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand(B, 784, generator=g) < torch.rand(784, generator=g)).to(torch.uint8)
+    eps = torch.randn(B, 64, generator=g)
+    u = torch.rand(B, 10, generator=g).clamp_min(1e-30)
+    return x, eps, u
+
+
+def test_full_size_known_answer_zero_weights():
+    """cfg4 batch (16 384 rows, 128 M-tiles per layer): KAT-1 holds exactly at full size."""
+    eng = make_engine(FULL, "bf16")
+    eng.params.zero_(); eng.params_updated()
+    x, eps, u = _full_inputs(FULL["batch"])
+    t = eng.forward_backward(x, eps=eps, gumbel_u=u).cpu().tolist()
+    assert rel(t[1], 543.4273895589971) < 1e-5 and abs(t[2]) < 1e-5 and rel(t[3], -2.302585092994046) < 1e-5
+    eng.close()
+
+
+def test_full_size_shard_sum_property():
+    """Size-independent property at the full cfg4 batch: the gradient of the batch mean is the sum of the
+    gradients of contiguous shards scaled by 1/B_global (what data parallelism relies on), and the loss
+    terms add up.  bf16 tensor-core path, fp32 accumulation order differs (atomics) -> 1e-3 on norms."""
+    B = FULL["batch"]
+    x, eps, u = _full_inputs(B)
+    eng = make_engine(FULL, "bf16"); eng.initialize(5)
+    eng.forward_backward(x, eps=eps, gumbel_u=u)
+    g_full = eng.grads.clone()
+    l_full = eng.loss_buf.clone()
+    acc = torch.zeros_like(g_full)
+    l_acc = torch.zeros(4, device="cuda")
+    cuts = [0, 5000, 11111, B]                                      # ragged shards (not multiples of a tile)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        l_acc += eng.forward_backward(x[a:b], eps=eps[a:b], gumbel_u=u[a:b], global_batch=B)
+        acc += eng.grads
+    torch.cuda.synchronize()
+    n = eng.params.numel()
+    assert ((acc[:n] - g_full[:n]).norm() / g_full[:n].norm()).item() < 1e-3
+    assert ((l_acc - l_full).abs() / l_full.abs().clamp_min(1.0)).max().item() < 1e-5   # loss, nll, kl, nent add up
+    eng.close()
+
+
+def test_full_size_matches_fp32_mode():
+    """At the full cfg4 batch the bf16 tensor-core step agrees with the fp32 CUDA-core validation mode on
+    the loss terms (2e-3) and, averaged over 16 384 samples, on the gradient direction."""
+    B = 4096                                                         # fp32 SIMT GEMMs are slow: a quarter of cfg4
+    cfg = dict(FULL, batch=B)
+    x, eps, u = _full_inputs(B)
+    a = make_engine(cfg, "bf16"); a.initialize(5)
+    b = make_engine(cfg, "fp32"); b.initialize(5)
+    la = a.forward_backward(x, eps=eps, gumbel_u=u).cpu()
+    lb = b.forward_backward(x, eps=eps, gumbel_u=u).cpu()
+    assert ((la - lb).abs() / lb.abs().clamp_min(1.0)).max().item() < 2e-3
+    n = a.params.numel()
+    cos = torch.nn.functional.cosine_similarity(a.grads[:n], b.grads[:n], dim=0).item()
+    assert cos > 0.999
+    a.close(); b.close()
