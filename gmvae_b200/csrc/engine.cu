@@ -21,6 +21,7 @@
 #include "epilogue.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_chain.cuh"
 #include "kernels.cuh"
 
 namespace gmvae {
@@ -109,7 +110,8 @@ struct LinView {
   const bf16* wt_bf16; int ld_wt;   // [out, ld_wt], already offset to column row0
 };
 
-enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32 };
+enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
+       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512 };
 // kernel classes of the per-launch profile (gmvae_profile_read)
 enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
        PC_COUNT = 7 };
@@ -150,6 +152,15 @@ struct gmvae_handle {
   int64_t reduced_upto = 0;              // floats of `grads` already handed to NCCL this step
   int64_t bucket_end[2] = {0, 0};        // flat offsets where bucket 0 (decoder) / 1 (encoder, prior) end
   int chunk_samples = 0;                 // objective M: samples per chunk of per-component rows
+  // GEMM chains (gemm_chain.cuh): while chain_on, tensor-core GEMMs are recorded as jobs of one launch
+  bool chain_on = false;
+  tc::ChainParams chain;
+  struct ChainWriter { const char* lo; const char* hi; int job; };
+  std::vector<ChainWriter> chain_writers;
+  int chain_tiles = 0;
+  int* chain_counters = nullptr; int chain_counter_cap = 0, chain_counter_next = 0;
+  long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
+  bool chain_flush_after = false;
   // graph
   cudaGraphExec_t graph_exec = nullptr;
 
@@ -288,6 +299,8 @@ static int plan(gmvae_handle* h) {
     if (c.model == GMVAE_MODEL_GMVAE) { plan_shadows(h, h->encoder_y); plan_shadows(h, h->prior_gmm); }
   }
   plan_buf(h, "infer.acc", ACC_SLOTS * 4);
+  h->chain_counter_cap = 64 * (int)((Bfull + 127) / 128 + 1);
+  plan_buf(h, "chain.counters", (size_t)h->chain_counter_cap * 4);
   return 0;
 }
 
@@ -316,8 +329,10 @@ static int profile_mark(gmvae_handle* h, cudaStream_t st, int cls) {
 // Hands grads[reduced_upto, upto) to NCCL on the side stream once everything enqueued on `st` so
 // far (which produced that range) has finished.  No-op outside gmvae_train_step / without a
 // communicator.  All ranks issue the same sequence of collectives.
+static int chain_flush(gmvae_handle* h, cudaStream_t st);
 static int comm_bucket(gmvae_handle* h, cudaStream_t st, int64_t upto) {
   if (!h->comm || h->world == 1 || !h->overlap_comm || upto <= h->reduced_upto) return 0;
+  GM_TRY(chain_flush(h, st));
   cudaEvent_t ev = h->comm_ev[h->comm_ev_next++ % 8];
   GM_CHECK_CUDA(cudaEventRecord(ev, st));
   GM_CHECK_CUDA(cudaStreamWaitEvent(h->comm_stream, ev, 0));
@@ -352,10 +367,131 @@ static bool tc_ok_dgrad(const gmvae_handle* h, const TD* dY, int64_t ldy, const 
          aligned16(dY) && aligned16(L.w_bf16);
 }
 
+
+// ============================================================================ GEMM chains
+// Launches the recorded jobs as one persistent kernel (gemm_chain.cuh).  Must be called before
+// anything else is enqueued on `st` that reads what the jobs write.
+static int chain_flush(gmvae_handle* h, cudaStream_t st) {
+  h->chain_flush_after = false;
+  if (h->chain.njobs == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    attr_set = true;
+  }
+  h->chain.counters = h->chain_counters;
+  h->chain.trace = (h->chain_trace && h->chain_launch_idx < 8) ? h->chain_trace + (size_t)h->chain_launch_idx * 64 * 16 : nullptr;
+  h->chain.trace_cta = h->chain_trace_cta;
+  h->chain_launch_idx++;
+  const int grid = std::min(h->chain_tiles, tc::num_sms());
+  GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+  h->chain.njobs = 0; h->chain_tiles = 0; h->chain_writers.clear();
+  h->launches++;
+  if (h->profiling) GM_TRY(profile_mark(h, st, 0 /*PC_TC_GEMM*/));
+  if (h->debug_flags & DBG_SYNC_EACH) GM_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+template <typename T, int MODE> static void writer_range(const EpiStore<T, MODE>& e, int M, const char*& lo, const char*& hi) {
+  lo = reinterpret_cast<const char*>(e.out); hi = lo + (int64_t)M * e.ld * sizeof(T);
+}
+template <typename T> static void writer_range(const EpiBCE<T>& e, int M, const char*& lo, const char*& hi) {
+  lo = reinterpret_cast<const char*>(e.dlogits); hi = lo + (int64_t)M * e.ld * sizeof(T);
+}
+template <typename T, typename HT> static void writer_range(const EpiReluMask<T, HT>& e, int M, const char*& lo, const char*& hi) {
+  lo = reinterpret_cast<const char*>(e.out); hi = lo + (int64_t)M * e.ld * sizeof(T);
+}
+static void writer_range(const EpiAtomicAdd&, int, const char*& lo, const char*& hi) { lo = hi = nullptr; }
+
+// Appends C = A1*B1 (+ A2*B2) with epilogue `epi` to the chain being recorded.  Dependencies on
+// earlier jobs of the chain are inferred from the operand pointers: an operand that lies in the
+// output of a recorded job makes this job wait for that job's row blocks.
+template <class Epi>
+static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& B1, const tc::Operand* A2, const tc::Operand* B2,
+                     int M, int N, int block_n, bool a_mn, bool b_mn, int split_k, const Epi& epi, cudaStream_t st) {
+  static_assert(tc::epi_kind<Epi>::value != tc::EK_NONE, "epilogue not supported by the chained kernel");
+  static_assert(sizeof(Epi) <= tc::CHAIN_EPI_BYTES, "epilogue parameters do not fit the job record");
+  const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M, tiles_n = (N + block_n - 1) / block_n;
+  // ---- dependencies
+  const void* reads[4] = {A1.ptr, A2 ? A2->ptr : nullptr, a_mn ? (const void*)B1.ptr : nullptr, epi.read_ptr()};
+  tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0, epi_dep = -1; bool need_flush = h->chain.njobs >= tc::CHAIN_MAX_JOBS;
+  for (int i = 0; i < 4 && !need_flush; ++i) {
+    const char* p = reinterpret_cast<const char*>(reads[i]);
+    if (!p) continue;
+    for (const auto& w : h->chain_writers) {
+      if (p < w.lo || p >= w.hi) continue;
+      const tc::ChainJob& P = h->chain.jobs[w.job];
+      if (p != w.lo || P.sig_base < 0) { need_flush = true; break; }          // offset view / no counters: order by kernel boundary
+      int dup = -1;
+      for (int d = 0; d < ndeps; ++d) if (deps[d].base == P.sig_base) dup = d;
+      if (dup >= 0) {
+        if (i == 3) { if (deps[dup].by_k) { need_flush = true; break; } epi_dep = dup; }
+        continue;
+      }
+      if (ndeps == tc::CHAIN_MAX_DEPS) { need_flush = true; break; }
+      if (i == 3) epi_dep = ndeps;
+      // by_k: this operand's rows are the contraction dimension (weight gradient over the batch)
+      const bool by_k = a_mn && i != 3;
+      deps[ndeps++] = tc::ChainDep{P.sig_base, tc::EPI_WARPS * P.tiles_n * P.num_splits, by_k ? 1 : 0, (P.M + tc::BLOCK_M - 1) / tc::BLOCK_M};
+    }
+  }
+  if (need_flush) { GM_TRY(chain_flush(h, st)); ndeps = 0; epi_dep = -1; }
+  // ---- the job
+  tc::ChainJob& J = h->chain.jobs[h->chain.njobs];
+  auto mk = [&](CUtensorMap* m, const tc::Operand& o, bool mn, int box_rows) -> int {
+    if (mn) return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.rows, (uint64_t)o.k, (uint64_t)o.ld, 64, tc::BLOCK_K);
+    return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.k, (uint64_t)o.rows, (uint64_t)o.ld, tc::BLOCK_K, (uint32_t)box_rows);
+  };
+  GM_TRY(mk(&J.a1, A1, a_mn, tc::BLOCK_M));
+  GM_TRY(mk(&J.b1, B1, b_mn, block_n));
+  J.kb1 = (A1.k + tc::BLOCK_K - 1) / tc::BLOCK_K; J.kb2 = 0;
+  if (A2 && B2) {
+    GM_TRY(mk(&J.a2, *A2, a_mn, tc::BLOCK_M));
+    GM_TRY(mk(&J.b2, *B2, b_mn, block_n));
+    J.kb2 = (A2->k + tc::BLOCK_K - 1) / tc::BLOCK_K;
+  } else {
+    J.a2 = J.a1; J.b2 = J.b1;
+  }
+  const int kb_total = J.kb1 + J.kb2;
+  if (split_k < 1) split_k = 1;
+  const int per = (kb_total + split_k - 1) / split_k;
+  split_k = (kb_total + per - 1) / per;
+  J.M = M; J.N = N; J.kb_per_split = per; J.num_splits = split_k;
+  J.block_n = block_n; J.a_mn = a_mn ? 1 : 0; J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
+  J.tiles_n = tiles_n; J.tiles_mn = tiles_m * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
+  J.ndeps = ndeps; J.epi_dep = epi_dep;
+  for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
+  const char *lo, *hi;
+  writer_range(epi, M, lo, hi);
+  J.sig_base = -1;
+  if (lo) {
+    if (h->chain_counter_next + tiles_m <= h->chain_counter_cap) {
+      J.sig_base = h->chain_counter_next; h->chain_counter_next += tiles_m;
+    } else {
+      h->chain_flush_after = true;     // out of counters: later readers are ordered by the kernel boundary
+    }
+    h->chain_writers.push_back({lo, hi, h->chain.njobs});
+  }
+  memset(J.epi, 0, sizeof(J.epi));
+  memcpy(J.epi, &epi, sizeof(Epi));
+  h->chain_tiles += J.total_tiles;
+  h->chain.njobs++;
+  if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
+  return 0;
+}
+template <class Epi> struct chainable { static constexpr bool value = tc::epi_kind<Epi>::value != tc::EK_NONE; };
+
 template <class Epi>
 static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Operand& B, const tc::Operand* A2,
                           const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
   int r;
+  if constexpr (chainable<Epi>::value) {
+    if (h->chain_on) {
+      const int bn = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : (N % 128 != 0 && N % 112 == 0) ? 112 : N <= 128 ? 128 : 256;
+      return chain_add(h, A, B, A2, B2, M, N, bn, false, false, 1, epi, st);
+    }
+  }
+  GM_TRY(chain_flush(h, st));
   if (N <= 16) r = tc::launch_gemm_tc<16, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N <= 32) r = tc::launch_gemm_tc<32, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
   else if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
@@ -384,21 +520,30 @@ static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinVi
     }
   }
   GM_REQUIRE(L2 == nullptr, "two-segment forward requires the tensor-core path");
+  GM_TRY(chain_flush(h, st));
   GM_CHECK_CUDA((launch_gemm_simt<TA, float, Epi>(A, lda, 1, L.w, L.ldw32, 1, M, L.out, L.in, 1, epi, st)));
   GM_LAUNCHED(h, st, PC_SIMT_GEMM);
   return 0;
 }
 
-// dX[M,in] = dY[M,out] * W^T
+// dX[M,in] = dY[M,out] * W^T  (+ dY2[M,out2] * W2^T: two layers reading the same input, one accumulator)
 template <typename TD, class Epi>
-static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const LinView& L, const Epi& epi, cudaStream_t st) {
+static int lin_dgrad(gmvae_handle* h, const TD* dY, int64_t ldy, int M, const LinView& L, const Epi& epi, cudaStream_t st,
+                     const TD* dY2 = nullptr, int64_t ldy2 = 0, const LinView* L2 = nullptr) {
   if constexpr (std::is_same<TD, bf16>::value) {
     bool ok = tc_ok_dgrad<TD>(h, dY, ldy, L);
+    if (L2) ok = ok && tc_ok_dgrad<TD>(h, dY2, ldy2, *L2) && L2->in == L.in;
     if (ok) {
       tc::Operand a{dY, ldy, M, kpad(L.out, ldy)}, b{L.w_bf16, L.ld_w, L.in, kpad(L.out, L.ld_w)};
+      if (L2) {
+        tc::Operand a2{dY2, ldy2, M, kpad(L2->out, ldy2)}, b2{L2->w_bf16, L2->ld_w, L2->in, kpad(L2->out, L2->ld_w)};
+        return tc_dispatch_kk(h, a, b, &a2, &b2, M, L.in, epi, st);
+      }
       return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.in, epi, st);
     }
   }
+  GM_REQUIRE(L2 == nullptr, "two-segment data gradient requires the tensor-core path");
+  GM_TRY(chain_flush(h, st));
   GM_CHECK_CUDA((launch_gemm_simt<TD, float, Epi>(dY, ldy, 1, L.w, 1, L.ldw32, M, L.in, L.out, 1, epi, st)));
   GM_LAUNCHED(h, st, PC_SIMT_GEMM);
   return 0;
@@ -420,6 +565,8 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
       // one wave of persistent CTAs: split the batch so that tiles * split ~ number of SMs,
       // keeping at least 4 k-blocks (256 samples) per split
       int split = std::max(1, std::min(std::max(1, kb / 4), tc::num_sms() / tiles));
+      if (h->chain_on) return chain_add(h, a, b, nullptr, nullptr, L.in, L.out, bn, true, true, split, epi, st);
+      GM_TRY(chain_flush(h, st));
       int r = bn == 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
               : bn == 128 ? tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
                           : tc::launch_gemm_tc<256, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st);
@@ -427,6 +574,7 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
       return r;
     }
   }
+  GM_TRY(chain_flush(h, st));
   const int tiles = ((L.in + SIMT_BM - 1) / SIMT_BM) * ((L.out + SIMT_BN - 1) / SIMT_BN);
   int split = std::max(1, std::min((M + 255) / 256, (4 * 148 + tiles - 1) / tiles));
   GM_CHECK_CUDA((launch_gemm_simt<TA, TD, EpiAtomicAdd>(A, 1, lda, dY, ldy, 1, L.in, L.out, M, split, epi, st)));
@@ -440,6 +588,7 @@ static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, fl
   int rows_per_block = std::max(64, (M * col_blocks + 2 * 148 - 1) / (2 * 148));
   rows_per_block = round_up(rows_per_block, 8);
   dim3 grid(col_blocks, (M + rows_per_block - 1) / rows_per_block);
+  GM_TRY(chain_flush(h, st));
   GM_CHECK_CUDA(launch_k(colsum_kernel<T>, grid, dim3(256), 0, st, true, dY, ldy, M, N, rows_per_block, db));
   GM_LAUNCHED(h, st, PC_BIAS_GRAD);
   return 0;
@@ -490,43 +639,37 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
   const int nl = (int)m.layers.size();
   const bool fuse = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
   bool bias_done = dout_bias_done;   // bias gradient of the layer whose output gradient we hold
-  {
-    const Linear& l = m.layers[nl - 1];
-    const bool first = nl == 1;
-    LinView L = view(h, l, 0, first ? in0_cols : -1);
-    const A* in = first ? in0 : b.hid[nl - 2];
-    int64_t ld = first ? ld0 : ldp(m.layers[nl - 2].out);
-    GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
-    if (!bias_done) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
-    bias_done = false;
-    if (!first) {
-      LinView Lf = view(h, l);
-      const int64_t ldh = ldp(m.layers[nl - 2].out);
-      // (layers below min_layer get their bias gradient from the caller)
-      float* cs = (fuse && nl - 2 >= min_layer && tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf)) ? h->grads + m.layers[nl - 2].b_off : nullptr;
-      EpiReluMask<A, A> epi{b.dhid[nl - 2], ldh, b.hid[nl - 2], ldh, cs};
-      GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
-      bias_done = cs != nullptr;
-    }
-  }
-  for (int i = nl - 2; i >= min_layer; --i) {
+  // Per layer, top down: first the data gradient (the next layer's input, so the chain of dependent
+  // GEMMs keeps moving), then the weight gradient of the same layer (its operands are complete by then).
+  for (int i = nl - 1; i >= min_layer; --i) {
     const Linear& l = m.layers[i];
     const bool first = i == 0;
     LinView L = view(h, l, 0, first ? in0_cols : -1);
     const A* in = first ? in0 : b.hid[i - 1];
-    int64_t ld = first ? ld0 : ldp(m.layers[i - 1].out);
-    const int64_t ldd = ldp(l.out);
-    GM_TRY((lin_wgrad<A, A>(h, in, ld, b.dhid[i], ldd, M, L, st)));
-    if (!bias_done) GM_TRY(bias_grad<A>(h, b.dhid[i], ldd, M, l.out, L.db, st));
-    bias_done = false;
+    const int64_t ld = first ? ld0 : ldp(m.layers[i - 1].out);
+    const bool top = i == nl - 1;
+    const A* dA = top ? nullptr : b.dhid[i];
+    const int64_t ldd = top ? ld_dout : ldp(l.out);
+    bool next_bias_done = false;
     if (!first) {
       LinView Lf = view(h, l);
       const int64_t ldh = ldp(m.layers[i - 1].out);
-      float* cs = (fuse && i - 1 >= min_layer && tc_ok_dgrad<A>(h, b.dhid[i], ldd, Lf)) ? h->grads + m.layers[i - 1].b_off : nullptr;
+      // (layers below min_layer get their bias gradient from the caller)
+      const bool ok = top ? tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf) : tc_ok_dgrad<A>(h, dA, ldd, Lf);
+      float* cs = (fuse && i - 1 >= min_layer && ok) ? h->grads + m.layers[i - 1].b_off : nullptr;
       EpiReluMask<A, A> epi{b.dhid[i - 1], ldh, b.hid[i - 1], ldh, cs};
-      GM_TRY((lin_dgrad<A>(h, b.dhid[i], ldd, M, Lf, epi, st)));
-      bias_done = cs != nullptr;
+      if (top) GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
+      else GM_TRY((lin_dgrad<A>(h, dA, ldd, M, Lf, epi, st)));
+      next_bias_done = cs != nullptr;
     }
+    if (top) {
+      GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
+      if (!bias_done) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
+    } else {
+      GM_TRY((lin_wgrad<A, A>(h, in, ld, dA, ldd, M, L, st)));
+      if (!bias_done) GM_TRY(bias_grad<A>(h, dA, ldd, M, l.out, L.db, st));
+    }
+    bias_done = next_bias_done;
   }
   return 0;
 }
@@ -576,6 +719,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
+    GM_TRY(chain_flush(h, st));
     GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, u, B, K,
                            1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc));
     GM_LAUNCHED(h, st, PC_HEADS);
@@ -622,7 +766,24 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
 }
 
 template <typename A>
+static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in, const float* u_in, cudaStream_t st);
+
+// Records the tensor-core GEMMs between two head kernels as one chained launch (gemm_chain.cuh).
+template <typename A>
 static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
+                                 const float* u_in, cudaStream_t st) {
+  h->chain.njobs = 0; h->chain_tiles = 0; h->chain_writers.clear(); h->chain_counter_next = 0; h->chain_launch_idx = 0;
+  h->chain_counters = h->buf<int>("chain.counters");
+  h->chain_on = std::is_same<A, bf16>::value && h->bf16_mode() && h->chain_counters && !(h->debug_flags & (DBG_NO_TC | DBG_NO_CHAIN));
+  if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
+  int r = forward_backward_body<A>(h, x_u8, B, Bg, eps_in, u_in, st);
+  if (r == 0) r = chain_flush(h, st);
+  h->chain_on = false; h->chain.njobs = 0;
+  return r;
+}
+
+template <typename A>
+static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
                                  const float* u_in, cudaStream_t st) {
   const gmvae_config& c = h->cfg;
   const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
@@ -658,6 +819,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   float* z_f32 = h->buf<float>("z_f32");
   {
     int64_t n = (int64_t)B * Z;
+    GM_TRY(chain_flush(h, st));
     GM_CHECK_CUDA(launch_k(head_z_fwd_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, true, (const float*)enc_out, eps,
                            (const float*)prior_out, prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, z_act, Zp, z_f32, acc));
     GM_LAUNCHED(h, st, PC_HEADS);
@@ -665,6 +827,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   float* dz_prior = h->buf<float>("dz_prior");
   if (prior_mode == 1) {
     const int warps = 4;
+    GM_TRY(chain_flush(h, st));
     GM_CHECK_CUDA(launch_k(gmp_prior_kernel, dim3((B + warps - 1) / warps), dim3(warps * 32), warps * K * sizeof(float), st, true,
                            (const float*)z_f32, (const float*)(h->params + h->loc_off), (const float*)(h->params + h->raw_scale_off),
                            (const float*)(h->params + h->mix_off), B, K, Z, inv_bg, dz_prior, h->grads + h->loc_off,
@@ -699,6 +862,7 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   {
     int64_t n = (int64_t)B * Z;
     enc_bias_fused = Z <= 256 && !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    GM_TRY(chain_flush(h, st));
     if (enc_bias_fused) {
       // also reduces db of the last encoder layer and of prior_gmm over the batch
       const int lanes = 256 / Z;
@@ -721,22 +885,26 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
     // y-columns of encoder_gmm layer 0: dW[D:] = y^T dh0 ; dy = dh0 W[D:]^T
     const A* dh0 = nl == 1 ? d_enc_out : enc.dhid[0];
     const int64_t ld_dh0 = nl == 1 ? Z2p : hid_ld(0);
-    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, dh0, ld_dh0, B, Ly, st)));
+    // dy = dh0 W[D:]^T + d_prior_out Wp^T : two K segments of one data-gradient GEMM (one accumulator)
+    const Linear& lp = h->prior_gmm.layers[0];
+    LinView Lp = view(h, lp);
+    const bool dy_two_seg = tc_ok_dgrad<A>(h, dh0, ld_dh0, Ly) && tc_ok_dgrad<A>(h, d_prior_out, Z2p, Lp) && !(h->debug_flags & DBG_NO_TWO_SEG);
     {
       EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
-      GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st)));
+      if (dy_two_seg) GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st, d_prior_out, Z2p, &Lp)));
+      else GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st)));
     }
-    // prior_gmm: dWp = y^T d_prior_out ; dbp ; dy += d_prior_out Wp^T
-    {
-      const Linear& l = h->prior_gmm.layers[0];
-      LinView Lp = view(h, l);
-      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
-      if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
+    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, dh0, ld_dh0, B, Ly, st)));
+    // prior_gmm: dWp = y^T d_prior_out ; dbp
+    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
+    if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
+    if (!dy_two_seg) {
       EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, d_prior_out, Z2p, B, Lp, e, st)));
     }
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    GM_TRY(chain_flush(h, st));
     GM_CHECK_CUDA(launch_k(head_y_bwd_kernel<A>, dim3(std::max(1, std::min(2 * tc::num_sms(), (B + 7) / 8))), dim3(256), 0, st, true,
                            (const float*)logits_y, (const float*)y_f32, (const float*)dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp,
                            ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
@@ -955,7 +1123,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   h->cfg = *cfg;
   const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
   h->debug_flags = dbg ? atoi(dbg) : 0;
-  g_use_pdl = !(h->debug_flags & 128);
+  g_use_pdl = !(h->debug_flags & DBG_NO_PDL);
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
   DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull;
@@ -1247,6 +1415,14 @@ int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int6
   if (q == 0) return 0;
   GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, eps, n_eps, u, n_u,
                          (const DeviceState*)h->state, (uint64_t)h->rank));
+  return 0;
+}
+
+// Test hook: clock64 stamps of CTA `cta` of every chained-GEMM launch of the following steps are written to
+// `trace` (device, 8 launches x 64 tiles x 16 int64; see gemm_chain.cuh).  Null switches it off.
+int gmvae_debug_chain_trace(gmvae_handle* h, long long* trace, int cta) {
+  GM_REQUIRE(h, "null handle");
+  h->chain_trace = trace; h->chain_trace_cta = cta;
   return 0;
 }
 

@@ -360,6 +360,9 @@ struct EpiStore {
   template <int BN>
   __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
   __device__ __forceinline__ float* colsum_dst() const { return nullptr; }
+  __host__ __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  const void* out_ptr() const { return out; }      // host: dependency inference of GEMM chains (gemm_chain.cuh)
+  const void* read_ptr() const { return MODE == EPI_ADDEND ? (const void*)addend : nullptr; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
@@ -435,6 +438,9 @@ struct EpiBCE {
   template <int BN>
   __device__ __forceinline__ void tile_begin(int n0, int N, float* sbias, int t, int nt) const { stage_bias<BN>(bias, n0, N, sbias, t, nt); }
   __device__ __forceinline__ float* colsum_dst() const { return colsum; }
+  __host__ __device__ __forceinline__ const float* bias_ptr() const { return bias; }
+  const void* out_ptr() const { return dlogits; }
+  const void* read_ptr() const { return nullptr; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
@@ -523,6 +529,9 @@ struct EpiReluMask {
   template <int BN>
   __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
   __device__ __forceinline__ float* colsum_dst() const { return colsum; }
+  __host__ __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
+  const void* out_ptr() const { return out; }
+  const void* read_ptr() const { return h; }
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx& ctx) const {
@@ -571,6 +580,9 @@ struct EpiAtomicAdd {
   template <int BN>
   __device__ __forceinline__ void tile_begin(int, int, float*, int, int) const {}
   __device__ __forceinline__ float* colsum_dst() const { return nullptr; }
+  __host__ __device__ __forceinline__ const float* bias_ptr() const { return nullptr; }
+  const void* out_ptr() const { return nullptr; }   // accumulated into the gradient buffer: consumed after the step's last GEMM only
+  const void* read_ptr() const { return nullptr; }
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int, int, int, bool, const EpiCtx&) const { return Pre<NV>(); }
   template <int NV>

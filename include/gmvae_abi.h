@@ -158,6 +158,9 @@ GMVAE_API int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB
 /* Test hook: the step's own noise generator (Philox4x32-10) writing n_eps N(0,1) draws and n_u
  * uniforms in the OPEN interval (0,1) into caller buffers (either may be NULL / 0). */
 GMVAE_API int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int64_t n_u, void* stream);
+/* Test hook: per-tile clock64 stamps of CTA `cta` of each chained-GEMM launch (8 launches x 64 tiles x 16 int64,
+ * device memory) for the following steps; null switches it off. */
+GMVAE_API int gmvae_debug_chain_trace(gmvae_handle* h, long long* trace, int cta);
 
 /* Per-launch profile: with profiling on, a CUDA event is recorded after every launch of the
  * (eager) step; read() returns the summed device time and launch count per kernel class:
