@@ -60,24 +60,30 @@ int num_sms() {
   return std::max(8, n - g_reserved_sms);
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
-                   uint32_t box_inner, uint32_t box_outer) {
-  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t> Key;
+// 2-D tensor of `elem_bytes`-wide elements (2: bf16, 4: fp32, 1: bytes), row-major [outer, inner] with `outer_stride`
+// elements between rows; box = {box_inner, box_outer}; swizzle span in bytes (128 / 64 / 0); out-of-bounds
+// elements read as zero and are not written.
+int make_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t outer_stride,
+              uint32_t box_inner, uint32_t box_outer, int swizzle) {
+  typedef std::tuple<const void*, int, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int> Key;
   static thread_local std::map<Key, CUtensorMap> cache;
-  Key key(ptr, inner, outer, outer_stride, box_inner, box_outer);
+  Key key(ptr, elem_bytes, inner, outer, outer_stride, box_inner, box_outer, swizzle);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return 0; }
   EncodeTiledFn fn = get_encode_fn();
   GM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   GM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base must be 16-byte aligned");
-  GM_REQUIRE((outer_stride * 2) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes");
+  GM_REQUIRE((outer_stride * (uint64_t)elem_bytes) % 16 == 0, "TMA operand row stride must be a multiple of 16 bytes");
   cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {outer_stride * 2};
+  cuuint64_t gstride[1] = {outer_stride * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                                                                      : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return -3;
@@ -85,6 +91,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t o
   if (cache.size() > 4096) cache.clear();
   cache[key] = *out;
   return 0;
+}
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
+                   uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap(out, ptr, 2, inner, outer, outer_stride, box_inner, box_outer, 128);
 }
 }  // namespace tc
 
@@ -403,6 +413,20 @@ template <typename T, typename HT> static void writer_range(const EpiReluMask<T,
 }
 static void writer_range(const EpiAtomicAdd&, int, const char*& lo, const char*& hi) { lo = hi = nullptr; }
 
+// What the chained kernel's epilogue writes through TMA (pointer, row stride, element size) and, for the
+// backward ReLU mask, reads through TMA.
+struct ChainIO { const void* out; int64_t ld; int elem; const void* opnd; int64_t ld_opnd; bool ok; };
+static ChainIO chain_io(const EpiStore<bf16, EPI_PLAIN>& e) { return {e.out, e.ld, 2, nullptr, 0, true}; }
+static ChainIO chain_io(const EpiStore<float, EPI_PLAIN>& e) { return {nullptr, e.ld, 4, nullptr, 0, true}; }     // per-row stores
+static ChainIO chain_io(const EpiBCE<bf16>& e) {
+  return {e.dlogits, e.ld, 2, nullptr, 0, e.row_weight == nullptr && e.row_sum == nullptr && e.x_row_div == 1};
+}
+static ChainIO chain_io(const EpiReluMask<bf16, bf16>& e) { return {e.out, e.ld, 2, e.h, e.ldh, true}; }
+static ChainIO chain_io(const EpiAtomicAdd& e) {
+  const bool tma = e.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0;
+  return {tma ? e.out : nullptr, e.ld, 4, nullptr, 0, true};
+}
+
 // Appends C = A1*B1 (+ A2*B2) with epilogue `epi` to the chain being recorded.  Dependencies on
 // earlier jobs of the chain are inferred from the operand pointers: an operand that lies in the
 // output of a recorded job makes this job wait for that job's row blocks.
@@ -472,6 +496,14 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
     }
     h->chain_writers.push_back({lo, hi, h->chain.njobs});
   }
+  // epilogue I/O through TMA: boxes of 32 rows x 64 bytes (one patch of the kernel)
+  const ChainIO io = chain_io(epi);
+  J.gw = 0; J.c = J.a1; J.d = J.a1;
+  if (io.out) {
+    J.gw = io.elem == 2 ? 2 : 1;
+    GM_TRY(tc::make_tmap(&J.d, io.out, io.elem, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld, io.elem == 2 ? 32 : 16, 32, 64));
+    if (io.opnd) GM_TRY(tc::make_tmap(&J.c, io.opnd, 2, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld_opnd, 32, 32, 64));
+  }
   memset(J.epi, 0, sizeof(J.epi));
   memcpy(J.epi, &epi, sizeof(Epi));
   h->chain_tiles += J.total_tiles;
@@ -486,8 +518,10 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
                           const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
   int r;
   if constexpr (chainable<Epi>::value) {
-    if (h->chain_on) {
-      const int bn = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : (N % 128 != 0 && N % 112 == 0) ? 112 : N <= 128 ? 128 : 256;
+    if (h->chain_on && chain_io(epi).ok) {
+      // outputs staged for TMA stores use tiles that are whole 64-column groups
+      const bool f32 = tc::epi_kind<Epi>::value == tc::EK_STORE_F32;
+      const int bn = (f32 && N <= 16) ? 16 : (f32 && N <= 32) ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
       return chain_add(h, A, B, A2, B2, M, N, bn, false, false, 1, epi, st);
     }
   }

@@ -37,7 +37,10 @@ constexpr int CHAIN_MAX_DEPS = 3;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 constexpr int CHAIN_EPI_BYTES = 128;
-constexpr int CHAIN_SMEM_BYTES = CHAIN_STAGES * CHAIN_STAGE_BYTES + 1024 + 256 + EPI_WARPS * PATCH_BYTES + 2 * 256 * 4 + 256 * 4;
+constexpr int CHAIN_PATCH_BYTES = 2048;   // per epilogue warp: 32 rows x 64 B, the box of one TMA store (SWIZZLE_64B like the tensor map)
+constexpr int CHAIN_CARVE_BYTES = CHAIN_STAGES * CHAIN_STAGE_BYTES + EPI_WARPS * CHAIN_PATCH_BYTES + 256 /*barriers*/ + 256 * 4 /*bias*/ + 256 * 4 /*column sums*/;
+constexpr int CHAIN_SMEM_BYTES = 232448;  // everything an SM offers one CTA (227 KB); the carve-out needs all but 768 bytes of it
+static_assert(CHAIN_CARVE_BYTES + 512 <= CHAIN_SMEM_BYTES, "shared-memory budget");
 
 // counters[base + row_block] >= target.  by_k = 0: the row block of the consumer's own tile;
 // by_k = 1 (weight gradients: the contraction runs over the batch): every row block its k-range covers.
@@ -45,6 +48,9 @@ struct ChainDep { int base, target, by_k, nblocks; };
 
 struct alignas(64) ChainJob {
   CUtensorMap a1, b1, a2, b2;
+  CUtensorMap c;                     // epilogue operand read by TMA (ReLU-mask source), box = one patch
+  CUtensorMap d;                     // output written by TMA store / reduce-add, box = one patch
+  int gw;                            // 16-column chunks per 64-byte patch row: 2 (bf16), 1 (fp32), 0: per-row stores
   int M, N, kb1, kb2, kb_per_split, num_splits;
   int block_n, a_mn, b_mn, kind;
   int tiles_n, tiles_mn, total_tiles, tile_base;
@@ -86,14 +92,69 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int mn
 
 struct ChainShared {
   uint8_t* smem; uint64_t* full_bar; uint64_t* empty_bar; uint64_t* tmem_full_bar; uint64_t* tmem_empty_bar;
-  uint8_t* patches; float* sbias_all; float* scs_all; uint32_t tmem_base;
+  uint8_t* patches; float* sbias_all; float* scs_all; uint32_t tmem_base; uint64_t* op_bar;
 };
+
+// ---- bulk-tensor stores (TMA): shared -> global, tracked in bulk async-groups of the issuing thread
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Patch addressing = the tensor map's swizzle: rows of RB bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B),
+// 16-byte unit u of row r.
+template <int RB> __device__ __forceinline__ uint32_t patch_unit(uint32_t patch, int r, int u) {
+  return RB == 128 ? patch + r * 128 + ((u ^ (r & 7)) << 4) : patch + r * 64 + ((u ^ ((r >> 1) & 3)) << 4);
+}
+
+// Column sums of a bf16 patch (32 rows) added into the CTA accumulator scs[0 .. RB/2).
+template <int RB>
+__device__ __forceinline__ void patch_colsum_bf16(uint32_t patch, float* scs, int ncols, int lane) {
+  constexpr int WORDS = RB / 4;                 // 32-bit words (column pairs) per row: 32 or 16
+  constexpr int GROUPS = 32 / WORDS;            // 1 or 2 row groups walked by different lanes
+  const int w = lane % WORDS, grp = lane / WORDS;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < 32 / GROUPS; ++i) {
+    const int r = grp * (32 / GROUPS) + i;
+    const uint32_t t = lds32(patch_unit<RB>(patch, r, w >> 2) + 4 * (w & 3));
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t));
+    s0 += f.x; s1 += f.y;
+  }
+  if (GROUPS == 2) { s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16); }
+  if (grp == 0) {
+    const uint32_t a = smem_addr(scs) + 8 * w;
+    if (2 * w < ncols && s0 != 0.f) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(s0) : "memory");
+    if (2 * w + 1 < ncols && s1 != 0.f) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a + 4), "f"(s1) : "memory");
+  }
+}
+
+__device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
+  lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+  hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+}
 
 // The epilogue warps' share of one job.  `it` counts the tiles this CTA has processed since the
 // start of the kernel (accumulator buffer = it & 1).
-template <class Epi>
-__device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* counters, const ChainShared& S, int& it, int warp, int lane,
-                                                   long long* trace, int jidx) {
+//
+// Output path (J.gw > 0): a warp owns the 32 rows of its TMEM lane quadrant and walks "groups" of
+// J.gw 16-column chunks.  Lane = row: the lane converts its row of a chunk and writes it into the
+// warp's patch at the position the output tensor map's swizzle expects; when the group is complete
+// one lane issues ONE bulk-tensor store (or reduce-add, for weight gradients) of the 32-row x 128-byte
+// (64-byte) box.  Global memory sees full lines from the TMA unit instead of 32-byte pieces from the
+// LSU (measured before: ~16 B/clk/SM, the limiter of the whole step), rows/columns beyond M/N are
+// clipped by the tensor map, and no st.global is issued by the epilogue warps at all.  The ReLU mask
+// source of the backward pass arrives the same way (TMA load of the box into the patch).
+template <class Epi, int KIND>
+__device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* counters, const ChainShared& S, int& it, uint32_t& op_phase,
+                                                   int warp, int lane, long long* trace, int jidx) {
   constexpr int CW = 16;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
   const int G = gridDim.x;
@@ -101,11 +162,14 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
   if (first >= J.total_tiles) return;
   const int M = J.M, N = J.N, BN = J.block_n, tiles_n = J.tiles_n, tiles_mn = J.tiles_mn;
   const int nchunk = BN / CW;
-  const int e = warp - 2, quad = warp & 3, half = e >> 2;
+  const int e = warp - 2, quad = warp & 3, slot = e >> 2;
   const int et = (int)threadIdx.x - 64;
   float* const cs_dst = epi.colsum_dst();
   const float* const bias = epi.bias_ptr();
   float* const scs_all = S.scs_all;
+  const uint32_t patch = smem_addr(S.patches + e * CHAIN_PATCH_BYTES);
+  uint64_t* const op_bar = S.op_bar + e;
+  const int gw = J.gw;
   int cs_n0 = -1;
   if (cs_dst) { for (int i = et; i < 256; i += EPI_WARPS * 32) scs_all[i] = 0.f; }
   auto cs_flush = [&]() {
@@ -120,8 +184,11 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
     const int mb = mn / tiles_n;
     const int m0 = mb * BLOCK_M, n0 = (mn - mb * tiles_n) * BN;
     const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
-    const int m = m0 + quad * 32 + lane;
-    float* sbias = S.sbias_all + (it & 1) * 256;
+    const int mrow0 = m0 + quad * 32;
+    const int m = mrow0 + lane;
+    float* sbias = S.sbias_all;
+    // bias of this tile's columns, staged once per tile (single buffer: every warp has finished the previous tile's reads)
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     {
       const uint32_t sb = smem_addr(sbias);
       for (int i = et; i < BN; i += EPI_WARPS * 32) sts32f(sb + 4 * i, (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f);
@@ -134,49 +201,177 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
       }
       cs_n0 = n0;
     }
-    EpiCtx ctx{S.patches + e * PATCH_BYTES, max(0, min(32, M - (m0 + quad * 32))), sbias, scs_all};
     const bool mvalid = m < M;
-    constexpr int CSTEP = EPI_WARPS / 4;
-    auto chunk_ok = [&](int ci) { return ci < nchunk && n0 + ci * CW < N; };
     const bool tr = trace && e == 0 && lane == 0 && it < 64;
     if (tr) { trace[16 * it + 6] = clock64(); trace[16 * it + 15] = jidx; trace[16 * it + 14] = l; }
-    typename Epi::template Pre<CW> pre_cur, pre_next;
     // The epilogue's own operand (ReLU mask source) is fetched ahead of the accumulator, i.e. possibly
     // before the TMA producer has seen this tile's dependencies: the warp checks the operand's producer itself.
     if (J.epi_dep >= 0) {
-      if (lane == 0) wait_counter(counters + J.deps[J.epi_dep].base + mb, J.deps[J.epi_dep].target);
+      if (lane == 0) { wait_counter(counters + J.deps[J.epi_dep].base + mb, J.deps[J.epi_dep].target); fence_proxy_async_global(); }
       __syncwarp();
     }
-    if (chunk_ok(half)) pre_cur = epi.template prefetch<CW>(m, n0 + half * CW, min(CW, N - (n0 + half * CW)), mvalid, ctx);
-    if (tr) trace[16 * it + 7] = clock64();
-    mbar_wait(&S.tmem_full_bar[as], ap);
-    tc_fence_after();
-    if (tr) trace[16 * it + 8] = clock64();
     const uint32_t taddr = S.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+    bool acc_ready = false;
+    auto wait_acc = [&]() {
+      if (!acc_ready) {
+        if (tr) trace[16 * it + 7] = clock64();
+        mbar_wait(&S.tmem_full_bar[as], ap);
+        tc_fence_after();
+        if (tr) trace[16 * it + 8] = clock64();
+        acc_ready = true;
+      }
+    };
+
+    if (KIND == EK_STORE_F32 || gw == 0) {
+     if constexpr (KIND == EK_STORE_F32 || KIND == EK_ATOMIC) {
+      // thin fp32 outputs (logits, [mu|raw], dz, dy) and weight gradients whose row stride is not a
+      // multiple of 16 bytes: each lane stores / accumulates its own row fragment
+      EpiCtx ctx{nullptr, max(0, min(32, M - mrow0)), sbias, scs_all};
+      wait_acc();
 #pragma unroll 1
-    for (int ci = half; chunk_ok(ci); ci += CSTEP) {
-      const int n = n0 + ci * CW;
-      const int nv = min(CW, N - n);
-      uint32_t r[CW];
-      ctx.sbias = sbias + ci * CW;
-      ctx.scs = scs_all + ci * CW;
-      tmem_ld16_issue(taddr + ci * CW, r);
-      const int cn = ci + CSTEP;
-      if (chunk_ok(cn)) pre_next = epi.template prefetch<CW>(m, n0 + cn * CW, min(CW, N - (n0 + cn * CW)), mvalid, ctx);
-      tmem_ld16_wait(r);
-      float v[CW];
+      for (int ci = slot; ci < nchunk && n0 + ci * CW < N; ci += 4) {
+        const int n = n0 + ci * CW;
+        uint32_t r[CW];
+        tmem_ld16_issue(taddr + ci * CW, r);
+        tmem_ld16_wait(r);
+        float v[CW];
 #pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
-      epi.template row<CW>(m, n, v, nv, mvalid, pre_cur, ctx);
-      pre_cur = pre_next;
+        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+        ctx.sbias = sbias + ci * CW;
+        typename Epi::template Pre<CW> pre;
+        epi.template row<CW>(m, n, v, min(CW, N - n), mvalid, pre, ctx);
+      }
+     }
+    } else if constexpr (KIND != EK_STORE_F32) {
+      const int ngroups = (nchunk + gw - 1) / gw;
+#pragma unroll 1
+      for (int g = slot; g < ngroups && n0 + g * gw * CW < N; g += 4) {
+        const int gcol = g * gw * CW;                        // first column of the group within the tile
+        // the previous bulk store issued from this patch must have read it before it is overwritten
+        if (lane == 0) bulk_wait_read0();
+        if constexpr (KIND == EK_RELUMASK) fence_proxy_async();   // this warp's earlier generic reads of the patch precede the TMA write
+        __syncwarp();
+        if constexpr (KIND == EK_RELUMASK) {
+          if (lane == 0) {
+            mbar_expect_tx(op_bar, (uint32_t)CHAIN_PATCH_BYTES);
+            tma_load_2d(&J.c, op_bar, S.patches + e * CHAIN_PATCH_BYTES, n0 + gcol, mrow0);
+          }
+        }
+        uint4 xq[2];
+        if constexpr (KIND == EK_BCE) {
+          // image bytes of this lane's row (16 per chunk), fetched ahead of the accumulator
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int n = n0 + gcol + c * CW;
+            xq[c] = make_uint4(0, 0, 0, 0);
+            if (c < gw && mvalid && n < N) {
+              const uint8_t* px = epi.x + (int64_t)m * epi.ldx + n;
+              if (n + CW <= N && (reinterpret_cast<uintptr_t>(px) & 15) == 0) {
+                xq[c] = *reinterpret_cast<const uint4*>(px);
+              } else {
+                uint8_t* b = reinterpret_cast<uint8_t*>(&xq[c]);
+                for (int i = 0; i < CW && n + i < N; ++i) b[i] = px[i];
+              }
+            }
+          }
+        }
+        wait_acc();
+        if constexpr (KIND == EK_RELUMASK) {
+          mbar_wait(op_bar, op_phase);
+          op_phase ^= 1;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int ci = g * gw + c;
+          if (c < gw && ci < nchunk && n0 + ci * CW < N) {       // warp-uniform
+            uint32_t r[CW];
+            tmem_ld16_issue(taddr + ci * CW, r);
+            float bb[CW];
+            if constexpr (KIND == EK_STORE_BF16 || KIND == EK_BCE) {
+              const uint32_t sb = smem_addr(sbias + ci * CW);
+#pragma unroll
+              for (int i = 0; i < CW; i += 4) { float4 t = lds128f(sb + 4 * i); bb[i] = t.x; bb[i + 1] = t.y; bb[i + 2] = t.z; bb[i + 3] = t.w; }
+            }
+            uint4 h0, h1;
+            if constexpr (KIND == EK_RELUMASK) {
+              h0 = lds128(patch_unit<64>(patch, lane, 2 * c)); h1 = lds128(patch_unit<64>(patch, lane, 2 * c + 1));
+            }
+            tmem_ld16_wait(r);
+            float v[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+            if constexpr (KIND == EK_ATOMIC) {
+              // fp32 rows of 64 bytes: one chunk per group, units 0 .. 3
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                sts128(patch_unit<64>(patch, lane, u),
+                       make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]), __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3])));
+            } else {
+              if constexpr (KIND == EK_STORE_BF16) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i) {
+                  v[i] = fmaf(v[i], epi.scale, bb[i]);
+                  if (epi.relu == 1) v[i] = fmaxf(v[i], 0.f);
+                  else if (epi.relu == 2) v[i] = sigmoid_f(v[i] + epi.shift);
+                }
+              } else if constexpr (KIND == EK_RELUMASK) {
+                const __nv_bfloat162* ph0 = reinterpret_cast<const __nv_bfloat162*>(&h0);
+                const __nv_bfloat162* ph1 = reinterpret_cast<const __nv_bfloat162*>(&h1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 a = __bfloat1622float2(ph0[k]), b = __bfloat1622float2(ph1[k]);
+                  v[2 * k] = a.x > 0.f ? v[2 * k] : 0.f; v[2 * k + 1] = a.y > 0.f ? v[2 * k + 1] : 0.f;
+                  v[8 + 2 * k] = b.x > 0.f ? v[8 + 2 * k] : 0.f; v[8 + 2 * k + 1] = b.y > 0.f ? v[8 + 2 * k + 1] : 0.f;
+                }
+              } else if constexpr (KIND == EK_BCE) {
+                const uint8_t* xb = reinterpret_cast<const uint8_t*>(&xq[c]);
+                const int nvalid = min(CW, N - (n0 + ci * CW));
+                float ll = 0.f;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) {
+                  const float lg = v[i] + epi.gen_bias + bb[i];
+                  // byte -> float without the conversion pipe: 2^23 + b is exact in fp32
+                  const float xv = __uint_as_float(0x4B000000u | (uint32_t)xb[i]) - 8388608.f;
+                  // bf16 mode only: fast intrinsics (exp(-|l|) in (0,1], log(1+e) with 1+e in (1,2]: abs error ~1e-7)
+                  const float ex = __expf(-fabsf(lg));
+                  const float sp = fmaxf(lg, 0.f) + __logf(1.f + ex);
+                  const float inv1pe = __fdividef(1.f, 1.f + ex);
+                  const float sg = lg >= 0.f ? inv1pe : ex * inv1pe;
+                  const bool ok = mvalid && i < nvalid;
+                  ll += ok ? fmaf(xv, lg, -sp) : 0.f;
+                  v[i] = ok ? (sg - xv) * epi.inv_bg : 0.f;
+                }
+                epi.partial += ll;
+              }
+              uint4 lo, hi;
+              pack16(v, lo, hi);
+              sts128(patch_unit<64>(patch, lane, 2 * c), lo); sts128(patch_unit<64>(patch, lane, 2 * c + 1), hi);
+            }
+          }
+        }
+        fence_proxy_async();                                  // generic-proxy writes to the patch -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (KIND == EK_ATOMIC) tma_reduce_add_2d(&J.d, patch, n0 + gcol, mrow0);
+          else tma_store_2d(&J.d, patch, n0 + gcol, mrow0);
+          bulk_commit();
+        }
+        if constexpr (KIND == EK_RELUMASK || KIND == EK_BCE) {
+          if (cs_dst) {
+            const int ncols = min(gw * CW, N - (n0 + gcol));
+            patch_colsum_bf16<64>(patch, scs_all + gcol, ncols, lane);
+          }
+        }
+      }
     }
     tc_fence_before();
     if (tr) trace[16 * it + 9] = clock64();
-    if (J.sig_base >= 0) fence_proxy_async_global();   // these rows are read back through TMA (async proxy) by later jobs
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&S.tmem_empty_bar[as]);
       if (J.sig_base >= 0) {
+        // rows stored by the bulk copies (async proxy) must be complete and visible before the row block is released
+        if constexpr (KIND != EK_STORE_F32) { bulk_wait0(); fence_proxy_async_global(); }
         __threadfence();
         atomicAdd(counters + J.sig_base + mb, 1);
       }
@@ -195,15 +390,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   constexpr int STAGES = CHAIN_STAGES, STAGE_BYTES = CHAIN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  if (smem - smem_raw + CHAIN_CARVE_BYTES > CHAIN_SMEM_BYTES) __trap();   // dynamic shared memory starts (at most 512 B off) a 1 KB boundary
+  uint8_t* patches = smem + STAGES * STAGE_BYTES;                       // 1024-byte aligned: TMA boxes with 64-byte swizzle
+  uint64_t* bars = reinterpret_cast<uint64_t*>(patches + EPI_WARPS * CHAIN_PATCH_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint8_t* patches = smem + STAGES * STAGE_BYTES + 256;
-  float* sbias_all = reinterpret_cast<float*>(patches + EPI_WARPS * PATCH_BYTES);
-  float* scs_all = sbias_all + 2 * 256;
+  uint64_t* op_bar = bars + 2 * STAGES + 4;                             // [EPI_WARPS] epilogue operand boxes
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(op_bar + EPI_WARPS);
+  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  float* scs_all = sbias_all + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x;
@@ -214,9 +411,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
       tma_prefetch_desc(&p.jobs[j].a1);
       tma_prefetch_desc(&p.jobs[j].b1);
       if (p.jobs[j].kb2 > 0) { tma_prefetch_desc(&p.jobs[j].a2); tma_prefetch_desc(&p.jobs[j].b2); }
+      if (p.jobs[j].gw > 0) tma_prefetch_desc(&p.jobs[j].d);
+      if (p.jobs[j].kind == EK_RELUMASK) tma_prefetch_desc(&p.jobs[j].c);
     }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
+    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&op_bar[s], 1);
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -293,8 +493,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         const ChainJob& J = p.jobs[j];
         const int tiles_mn = J.tiles_mn, kb_total = J.kb1 + J.kb2;
         const int a_mn = J.a_mn, b_mn = J.b_mn;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-                               ((uint32_t)(J.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+                                ((uint32_t)(BLOCK_M >> 4) << 24);
         const uint64_t a_step = a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         const uint64_t b_step = b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         const int first = ((c - J.tile_base) % G + G) % G;
@@ -302,6 +502,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
           const int z = l / tiles_mn;
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
           const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+          // a ragged last n-tile runs a narrower MMA (N multiple of 16): the zero-filled columns are not multiplied
+          const int n0 = ((l - z * tiles_mn) % J.tiles_n) * J.block_n;
+          const int n_eff = min(J.block_n, (J.N - n0 + 15) & ~15);
+          const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
           const bool tr = trace && it < 64;
           if (tr) trace[16 * it + 3] = clock64();
           mbar_wait(&tmem_empty_bar[as], ap ^ 1);
@@ -328,20 +532,22 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     }
   } else {
     // ===== epilogue warps =====
-    ChainShared S{smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, patches, sbias_all, scs_all, tmem_base};
+    ChainShared S{smem, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, patches, sbias_all, scs_all, tmem_base, op_bar};
     int it = 0;
+    uint32_t op_phase = 0;
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>>(J, p.counters, S, it, warp, lane, trace, j); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>>(J, p.counters, S, it, warp, lane, trace, j); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>>(J, p.counters, S, it, warp, lane, trace, j); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>>(J, p.counters, S, it, warp, lane, trace, j); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd>(J, p.counters, S, it, warp, lane, trace, j); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
         default: break;
       }
     }
   }
+  if (warp >= 2 && lane == 0) bulk_wait0();     // outstanding bulk stores read this CTA's shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

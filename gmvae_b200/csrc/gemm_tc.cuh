@@ -406,6 +406,9 @@ EncodeTiledFn get_encode_fn();
 // box = {box_inner (<= 64), box_outer}, 128-byte swizzle, out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t outer_stride,
                    uint32_t box_inner, uint32_t box_outer);
+// general form: element size 1/2/4 bytes, swizzle span 128/64/0 bytes
+int make_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t outer_stride,
+              uint32_t box_inner, uint32_t box_outer, int swizzle);
 
 // Operand description given to launch_gemm_tc: a row-major bf16 matrix.
 //   K-major operand  : stored [rows(M or N), K],  ld = row stride
