@@ -754,8 +754,13 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
     GM_TRY(chain_flush(h, st));
-    GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, u, B, K,
-                           1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc));
+    if (std::is_same<A, bf16>::value && K <= 16 && Kp <= 16) {
+      GM_CHECK_CUDA(launch_k(head_y_fwd_row_kernel, dim3((B + 127) / 128), dim3(128), 0, st, true, (const float*)logits_y, u, B, K,
+                             1.f / c.temperature, inv_bg, y_f32, reinterpret_cast<bf16*>(y_act), Kp, acc));
+    } else {
+      GM_CHECK_CUDA(launch_k(head_y_fwd_kernel<A>, dim3((B + 7) / 8), dim3(256), 0, st, true, (const float*)logits_y, u, B, K,
+                             1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc));
+    }
     GM_LAUNCHED(h, st, PC_HEADS);
     // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
     {
@@ -854,8 +859,16 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   {
     int64_t n = (int64_t)B * Z;
     GM_TRY(chain_flush(h, st));
-    GM_CHECK_CUDA(launch_k(head_z_fwd_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, true, (const float*)enc_out, eps,
-                           (const float*)prior_out, prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, z_act, Zp, z_f32, acc));
+    const bool v4 = std::is_same<A, bf16>::value && Z % 4 == 0 && Z <= 256 && aligned16(eps) && aligned16(enc_out) &&
+                    (prior_mode != 2 || aligned16(prior_out));
+    if (v4) {
+      const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256, 8 * tc::num_sms());
+      GM_CHECK_CUDA(launch_k(head_z_fwd_v4_kernel, dim3(blocks), dim3(256), 0, st, true, (const float*)enc_out, eps, (const float*)prior_out,
+                             prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, reinterpret_cast<bf16*>(z_act), Zp, z_f32, acc));
+    } else {
+      GM_CHECK_CUDA(launch_k(head_z_fwd_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, true, (const float*)enc_out, eps,
+                             (const float*)prior_out, prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, z_act, Zp, z_f32, acc));
+    }
     GM_LAUNCHED(h, st, PC_HEADS);
   }
   float* dz_prior = h->buf<float>("dz_prior");
@@ -897,7 +910,17 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     int64_t n = (int64_t)B * Z;
     enc_bias_fused = Z <= 256 && !(h->debug_flags & DBG_NO_FUSED_COLSUM);
     GM_TRY(chain_flush(h, st));
-    if (enc_bias_fused) {
+    const bool v4 = std::is_same<A, bf16>::value && enc_bias_fused && Z % 4 == 0 && aligned16(eps) && aligned16(enc_out) && aligned16(dz) &&
+                    (prior_mode != 2 || aligned16(prior_out)) && (prior_mode != 1 || aligned16(dz_prior));
+    if (v4) {
+      // rows are spread over 4 CTAs per SM: every thread sees 1-2 rows, the column sums cost 4Z atomics per CTA
+      const int rpi = 256 / (Z / 4);
+      const int blocks = std::max(1, std::min(4 * tc::num_sms(), (B + rpi - 1) / rpi));
+      GM_CHECK_CUDA(launch_k(head_z_bwd_v4_kernel, dim3(blocks), dim3(256), (size_t)16 * 256 * sizeof(float), st, true, (const float*)enc_out,
+                             eps, (const float*)prior_out, (const float*)dz, (const float*)dz_prior, prior_mode, B, Z, c.raw_sigma_bias,
+                             c.sigma_min, inv_bg, reinterpret_cast<bf16*>(d_enc_out), reinterpret_cast<bf16*>(d_prior_out), Z2p,
+                             h->grads + enc_last.b_off, gm ? h->grads + h->prior_gmm.layers[0].b_off : (float*)nullptr));
+    } else if (enc_bias_fused) {
       // also reduces db of the last encoder layer and of prior_gmm over the batch
       const int lanes = 256 / Z;
       const int blocks = std::max(1, std::min(2 * tc::num_sms(), (B + lanes - 1) / lanes));
@@ -939,9 +962,15 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
     GM_TRY(chain_flush(h, st));
-    GM_CHECK_CUDA(launch_k(head_y_bwd_kernel<A>, dim3(std::max(1, std::min(2 * tc::num_sms(), (B + 7) / 8))), dim3(256), 0, st, true,
-                           (const float*)logits_y, (const float*)y_f32, (const float*)dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp,
-                           ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
+    if (std::is_same<A, bf16>::value && K <= 16 && Kp <= 16) {
+      GM_CHECK_CUDA(launch_k(head_y_bwd_row_kernel, dim3(std::max(1, std::min(tc::num_sms(), (B + 127) / 128))), dim3(128), 0, st, true,
+                             (const float*)logits_y, (const float*)y_f32, (const float*)dy, B, K, 1.f / c.temperature, inv_bg,
+                             reinterpret_cast<bf16*>(dlogits_y), Kp, ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
+    } else {
+      GM_CHECK_CUDA(launch_k(head_y_bwd_kernel<A>, dim3(std::max(1, std::min(2 * tc::num_sms(), (B + 7) / 8))), dim3(256), 0, st, true,
+                             (const float*)logits_y, (const float*)y_f32, (const float*)dy, B, K, 1.f / c.temperature, inv_bg, dlogits_y, Kp,
+                             ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
+    }
     GM_LAUNCHED(h, st, PC_HEADS);
     GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st, ey_bias_fused)));
   }

@@ -336,6 +336,244 @@ __global__ void head_z_bwd_cs_kernel(const float* __restrict__ enc_out, const fl
   }
 }
 
+// ---- vectorised / row-per-thread variants of the heads (the bf16 training step at the reference's sizes) ----
+// The kernels above keep one element (or one warp per row) per thread, which at a batch of 16 384 is bound by
+// the latency of a handful of dependent 4-byte loads.  These variants move 16 bytes per load:
+//   z heads: thread <-> 4 consecutive latent dimensions of one row (Z % 4 == 0, Z <= 256, 16-byte aligned rows);
+//   y heads: thread <-> one row, the K <= 16 mixture components in registers (no warp shuffles).
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) { return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d)); }
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void head_z_fwd_v4_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
+                                     const float* __restrict__ prior_out, int prior_mode, int B, int Z, float c,
+                                     float sigma_min, float inv_bg, bf16* __restrict__ z_act, int ld_z, float* __restrict__ z_f32,
+                                     float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float scratch[32];
+  const int tpr = Z >> 2;                                  // threads per row
+  const int64_t total = (int64_t)B * tpr;
+  float kl = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(t / tpr), j = (int)(t % tpr) * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(enc_out + (int64_t)b * 2 * Z + j);
+    const float4 raw = *reinterpret_cast<const float4*>(enc_out + (int64_t)b * 2 * Z + Z + j);
+    const float4 e4 = *reinterpret_cast<const float4*>(eps + (int64_t)b * Z + j);
+    float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp;
+    if (prior_mode == 2) {
+      mp = *reinterpret_cast<const float4*>(prior_out + (int64_t)b * 2 * Z + j);
+      rp = *reinterpret_cast<const float4*>(prior_out + (int64_t)b * 2 * Z + Z + j);
+    }
+    const float* MU = &mu.x; const float* RAW = &raw.x; const float* E = &e4.x; const float* MP = &mp.x; const float* RP = &rp.x;
+    float z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float sg = fmaxf(softplus_f(RAW[q] + c), sigma_min);
+      z[q] = fmaf(sg, E[q], MU[q]);
+      const float logq = -0.5f * E[q] * E[q] - logf(sg);
+      float logp = 0.f;
+      if (prior_mode == 0) {
+        logp = -0.5f * z[q] * z[q];
+      } else if (prior_mode == 2) {
+        const float sp = fmaxf(softplus_f(RP[q] + c), sigma_min);
+        const float tt = (z[q] - MP[q]) / sp;
+        logp = -0.5f * tt * tt - logf(sp);
+      }
+      kl += logq - logp;
+    }
+    *reinterpret_cast<uint2*>(z_act + (int64_t)b * ld_z + j) = pack_bf16x4(z[0], z[1], z[2], z[3]);
+    if (z_f32) *reinterpret_cast<float4*>(z_f32 + (int64_t)b * Z + j) = make_float4(z[0], z[1], z[2], z[3]);
+  }
+  float s = block_sum(kl, scratch);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_KL, s * inv_bg);
+}
+
+// backward of the z head + the bias gradients of the last encoder layer and of prior_gmm (column sums of
+// the values as stored).  blockDim.x = 256; dynamic shared memory = 16 * 256 floats.
+__global__ void head_z_bwd_v4_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps,
+                                     const float* __restrict__ prior_out, const float* __restrict__ dz_dec,
+                                     const float* __restrict__ dz_prior, int prior_mode, int B, int Z, float c, float sigma_min,
+                                     float inv_bg, bf16* __restrict__ d_enc_out, bf16* __restrict__ d_prior_out, int ld_out,
+                                     float* __restrict__ db_enc, float* __restrict__ db_prior) {
+  griddep_wait();
+  griddep_launch();
+  extern __shared__ float red[];                        // [4 pieces][rows per iteration][Z]
+  const int tpr = Z >> 2, rpi = blockDim.x / tpr;       // threads per row, rows per block iteration
+  const int jt = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  const int j = jt * 4;
+  float s[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[p][q] = 0.f;
+  if (rl < rpi) {
+    for (int b = blockIdx.x * rpi + rl; b < B; b += gridDim.x * rpi) {
+      const float4 mu = *reinterpret_cast<const float4*>(enc_out + (int64_t)b * 2 * Z + j);
+      const float4 raw = *reinterpret_cast<const float4*>(enc_out + (int64_t)b * 2 * Z + Z + j);
+      const float4 e4 = *reinterpret_cast<const float4*>(eps + (int64_t)b * Z + j);
+      const float4 dzd = *reinterpret_cast<const float4*>(dz_dec + (int64_t)b * Z + j);
+      float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp, dzp = mp;
+      if (prior_mode == 2) {
+        mp = *reinterpret_cast<const float4*>(prior_out + (int64_t)b * 2 * Z + j);
+        rp = *reinterpret_cast<const float4*>(prior_out + (int64_t)b * 2 * Z + Z + j);
+      } else if (prior_mode == 1) {
+        dzp = *reinterpret_cast<const float4*>(dz_prior + (int64_t)b * Z + j);
+      }
+      const float* MU = &mu.x; const float* RAW = &raw.x; const float* E = &e4.x; const float* DZ = &dzd.x;
+      const float* MP = &mp.x; const float* RP = &rp.x; const float* DZP = &dzp.x;
+      float g0[4], g1[4], a0[4], a1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float spq = softplus_f(RAW[q] + c);
+        const float sg = fmaxf(spq, sigma_min);
+        const float z = fmaf(sg, E[q], MU[q]);
+        float dz = DZ[q];
+        a0[q] = 0.f; a1[q] = 0.f;
+        if (prior_mode == 0) {
+          dz += z * inv_bg;
+        } else if (prior_mode == 1) {
+          dz += DZP[q];
+        } else {
+          const float spp = softplus_f(RP[q] + c);
+          const float sp = fmaxf(spp, sigma_min);
+          const float d = z - MP[q];
+          const float isp2 = 1.f / (sp * sp);
+          dz += d * isp2 * inv_bg;
+          const float dsp = (1.f / sp - d * d * isp2 / sp) * inv_bg;
+          a0[q] = bf16_round(-d * isp2 * inv_bg);
+          a1[q] = bf16_round(spp >= sigma_min ? dsp * sigmoid_f(RP[q] + c) : 0.f);
+        }
+        const float dsg = dz * E[q] - inv_bg / sg;
+        g0[q] = bf16_round(dz);
+        g1[q] = bf16_round(spq >= sigma_min ? dsg * sigmoid_f(RAW[q] + c) : 0.f);
+        s[0][q] += g0[q]; s[1][q] += g1[q]; s[2][q] += a0[q]; s[3][q] += a1[q];   // sums of the values as stored
+      }
+      *reinterpret_cast<uint2*>(d_enc_out + (int64_t)b * ld_out + j) = pack_bf16x4(g0[0], g0[1], g0[2], g0[3]);
+      *reinterpret_cast<uint2*>(d_enc_out + (int64_t)b * ld_out + Z + j) = pack_bf16x4(g1[0], g1[1], g1[2], g1[3]);
+      if (prior_mode == 2) {
+        *reinterpret_cast<uint2*>(d_prior_out + (int64_t)b * ld_out + j) = pack_bf16x4(a0[0], a0[1], a0[2], a0[3]);
+        *reinterpret_cast<uint2*>(d_prior_out + (int64_t)b * ld_out + Z + j) = pack_bf16x4(a1[0], a1[1], a1[2], a1[3]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      *reinterpret_cast<float4*>(red + ((size_t)p * rpi + rl) * Z + j) = make_float4(s[p][0], s[p][1], s[p][2], s[p][3]);
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < 4 * Z; col += blockDim.x) {
+    const int p = col / Z, jj = col % Z;
+    if (p >= 2 && prior_mode != 2) continue;
+    float t = 0.f;
+    for (int l = 0; l < rpi; ++l) t += red[((size_t)p * rpi + l) * Z + jj];
+    if (t != 0.f) atomicAdd((p < 2 ? db_enc : db_prior) + (p & 1) * Z + jj, t);
+  }
+}
+
+// q(y|x) head forward, one row per thread (K <= 16)
+__global__ void head_y_fwd_row_kernel(const float* __restrict__ logits, const float* __restrict__ u, int B, int K, float inv_T,
+                                      float inv_bg, float* __restrict__ y_f32, bf16* __restrict__ y_act, int ld_yact,
+                                      float* __restrict__ acc) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float scratch[32];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float ent = 0.f;
+  if (row < B) {
+    float l[16], a[16];
+    float ml = -INFINITY, ma = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      l[k] = -INFINITY; a[k] = -INFINITY;
+      if (k < K) {
+        l[k] = logits[(int64_t)row * K + k];
+        a[k] = u ? (l[k] - logf(-logf(u[(int64_t)row * K + k]))) * inv_T : l[k];
+      }
+      ml = fmaxf(ml, l[k]); ma = fmaxf(ma, a[k]);
+    }
+    float sl = 0.f, sa = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) { a[k] = expf(a[k] - ma); sl += expf(l[k] - ml); sa += a[k]; }
+    const float lse = ml + logf(sl), inv_sa = 1.f / sa;
+    float y[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      y[k] = 0.f;
+      if (k < K) {
+        const float logp = l[k] - lse;
+        ent += expf(logp) * logp;
+        y[k] = a[k] * inv_sa;
+        y_f32[(int64_t)row * K + k] = y[k];
+      }
+    }
+    // zero-padded bf16 operand row (ld_yact is a multiple of 8, at most 16)
+    uint4* dst = reinterpret_cast<uint4*>(y_act + (int64_t)row * ld_yact);
+    dst[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    if (ld_yact > 8) dst[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+  }
+  float s = block_sum(ent, scratch);
+  if (threadIdx.x == 0 && s != 0.f) acc_add(acc, ACC_NENT, s * inv_bg);
+}
+
+// q(y|x) head backward, one row per thread (K <= 16), fused bias gradient of encoder_y's last layer
+__global__ void head_y_bwd_row_kernel(const float* __restrict__ logits, const float* __restrict__ y_f32,
+                                      const float* __restrict__ dy, int B, int K, float inv_T, float inv_bg,
+                                      bf16* __restrict__ dlogits, int ld_out, float* __restrict__ db) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float cs_s[16];
+  if (threadIdx.x < 16) cs_s[threadIdx.x] = 0.f;
+  __syncthreads();
+  float cs[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cs[k] = 0.f;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < B; row += gridDim.x * blockDim.x) {
+    float l[16], y[16], g[16];
+    float ml = -INFINITY, ydy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      l[k] = -INFINITY; y[k] = 0.f; g[k] = 0.f;
+      if (k < K) {
+        l[k] = logits[(int64_t)row * K + k];
+        y[k] = y_f32[(int64_t)row * K + k];
+        g[k] = dy ? dy[(int64_t)row * K + k] : 0.f;
+      }
+      ml = fmaxf(ml, l[k]);
+      ydy += y[k] * g[k];
+    }
+    float sl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) sl += expf(l[k] - ml);
+    const float lse = ml + logf(sl);
+    float plogp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) { l[k] -= lse; plogp += expf(l[k]) * l[k]; }
+    float o[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      o[k] = 0.f;
+      if (k < K) {
+        o[k] = bf16_round(y[k] * (g[k] - ydy) * inv_T + expf(l[k]) * (l[k] - plogp) * inv_bg);
+        cs[k] += o[k];
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dlogits + (int64_t)row * ld_out);
+    dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+  }
+  if (db) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float t = warp_sum(cs[k]);
+      if ((threadIdx.x & 31) == 0 && k < K && t != 0.f) atomicAdd(cs_s + k, t);
+    }
+    __syncthreads();
+    if (threadIdx.x < K && cs_s[threadIdx.x] != 0.f) atomicAdd(db + threadIdx.x, cs_s[threadIdx.x]);
+  }
+}
+
 // ---- inference helpers (gmvae.py:109-188, vae.py:80-123) ------------------------------------------
 // z_mean = mu, z_sample = mu + sigma eps from the encoder's [mu|raw] output
 __global__ void encode_out_kernel(const float* __restrict__ enc_out, const float* __restrict__ eps, int B, int Z, float c, float sigma_min,
