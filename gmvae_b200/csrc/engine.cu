@@ -6,6 +6,7 @@
 // (runners.py:183), expressed as a fixed sequence of kernels on the caller's stream.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -104,8 +105,7 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 struct Linear {
   int in = 0, out = 0;
   int64_t w_off = 0, b_off = 0;
-  bf16* w_bf16 = nullptr;  int ld_w = 0;    // [in, ld_w]
-  bf16* wt_bf16 = nullptr; int ld_wt = 0;   // [out, ld_wt]
+  bf16* w_bf16 = nullptr;  int ld_w = 0;    // [in, ld_w]: K-major B of the data-gradient GEMM, MN-major B of the forward GEMM
 };
 struct Mlp {
   std::string name;
@@ -116,12 +116,13 @@ struct Mlp {
 struct LinView {
   const float* w; float* dw; const float* b; float* db;
   int in, out, ldw32;               // fp32 row stride (= full `out`)
-  const bf16* w_bf16; int ld_w;     // [in, ld_w]
-  const bf16* wt_bf16; int ld_wt;   // [out, ld_wt], already offset to column row0
+  const bf16* w_bf16; int ld_w;     // [in, ld_w], already offset to row row0
 };
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
-       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512 };
+       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512,
+       DBG_RELU_BITS = 2048 /* 1-bit ReLU masks between the chained forward and backward jobs: measured 1 % slower than
+                               reading the bf16 activation through TMA, kept as an experiment */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
 enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
        PC_COUNT = 7 };
@@ -171,6 +172,8 @@ struct gmvae_handle {
   int* chain_counters = nullptr; int chain_counter_cap = 0, chain_counter_next = 0;
   long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
   bool chain_flush_after = false;
+  bool last_gemm_chained = false;                 // set by the GEMM dispatch: the last GEMM became a job of the chain
+  std::map<const void*, bool> relu_bits_valid;    // hidden activation -> its 1-bit ReLU mask was written this step
   // graph
   cudaGraphExec_t graph_exec = nullptr;
 
@@ -216,14 +219,14 @@ static void plan_mlp_bufs(gmvae_handle* h, const Mlp& m, size_t B, size_t asz) {
   for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
     plan_buf(h, m.name + ".h" + std::to_string(i), B * round_up(m.layers[i].out, 8) * asz);
     plan_buf(h, m.name + ".dh" + std::to_string(i), B * round_up(m.layers[i].out, 8) * asz);
+    plan_buf(h, m.name + ".bits" + std::to_string(i), (size_t)round_up((int)B, 32) * (size_t)((m.layers[i].out + 31) / 32) * 4);   // 1-bit ReLU masks (chained kernel)
   }
 }
 
 static void plan_shadows(gmvae_handle* h, Mlp& m) {
   for (auto& l : m.layers) {
-    l.ld_w = round_up(l.out, 8); l.ld_wt = round_up(l.in, 8);
+    l.ld_w = round_up(l.out, 8);
     plan_buf(h, "shadow.w." + std::to_string(l.w_off), (size_t)l.in * l.ld_w * 2);
-    plan_buf(h, "shadow.wt." + std::to_string(l.w_off), (size_t)l.out * l.ld_wt * 2);
   }
 }
 
@@ -322,7 +325,6 @@ static LinView view(const gmvae_handle* h, const Linear& l, int row0 = 0, int ro
   v.b = h->params + l.b_off; v.db = h->grads + l.b_off;
   v.in = rows; v.out = l.out; v.ldw32 = l.out;
   v.w_bf16 = l.w_bf16 ? l.w_bf16 + (int64_t)row0 * l.ld_w : nullptr; v.ld_w = l.ld_w;
-  v.wt_bf16 = l.wt_bf16 ? l.wt_bf16 + row0 : nullptr; v.ld_wt = l.ld_wt;
   return v;
 }
 
@@ -368,8 +370,8 @@ static inline int kpad(int k, int64_t ld) { return (int)std::min<int64_t>(ld, ro
 
 template <typename TA>
 static bool tc_ok_fwd(const gmvae_handle* h, const TA* A, int64_t lda, const LinView& L) {
-  return std::is_same<TA, bf16>::value && h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.wt_bf16 && lda % 8 == 0 &&
-         aligned16(A) && aligned16(L.wt_bf16);
+  return std::is_same<TA, bf16>::value && h->bf16_mode() && !(h->debug_flags & DBG_NO_TC) && L.w_bf16 && lda % 8 == 0 &&
+         aligned16(A) && aligned16(L.w_bf16);
 }
 template <typename TD>
 static bool tc_ok_dgrad(const gmvae_handle* h, const TD* dY, int64_t ldy, const LinView& L) {
@@ -383,6 +385,7 @@ static bool tc_ok_dgrad(const gmvae_handle* h, const TD* dY, int64_t ldy, const 
 // anything else is enqueued on `st` that reads what the jobs write.
 static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain_flush_after = false;
+  h->last_gemm_chained = false;
   if (h->chain.njobs == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -508,30 +511,36 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   memcpy(J.epi, &epi, sizeof(Epi));
   h->chain_tiles += J.total_tiles;
   h->chain.njobs++;
+  h->last_gemm_chained = true;
   if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
   return 0;
 }
 template <class Epi> struct chainable { static constexpr bool value = tc::epi_kind<Epi>::value != tc::EK_NONE; };
 
-template <class Epi>
+template <class Epi, bool B_MN = false>
 static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Operand& B, const tc::Operand* A2,
                           const tc::Operand* B2, int M, int N, const Epi& epi, cudaStream_t st) {
   int r;
   if constexpr (chainable<Epi>::value) {
     if (h->chain_on && chain_io(epi).ok) {
-      // outputs staged for TMA stores use tiles that are whole 64-column groups
+      // outputs staged for TMA stores use tiles that are whole 32-column groups; MN-major B comes in 64-column slabs
       const bool f32 = tc::epi_kind<Epi>::value == tc::EK_STORE_F32;
-      const int bn = (f32 && N <= 16) ? 16 : (f32 && N <= 32) ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
-      return chain_add(h, A, B, A2, B2, M, N, bn, false, false, 1, epi, st);
+      const int bn = (!B_MN && f32 && N <= 16) ? 16 : (!B_MN && f32 && N <= 32) ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+      return chain_add(h, A, B, A2, B2, M, N, bn, false, B_MN, 1, epi, st);
     }
   }
   GM_TRY(chain_flush(h, st));
-  if (N <= 16) r = tc::launch_gemm_tc<16, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else if (N <= 32) r = tc::launch_gemm_tc<32, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else if (N % 128 != 0 && N % 112 == 0) r = tc::launch_gemm_tc<112, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else if (N <= 128 || (h->debug_flags & DBG_BN128)) r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
-  else r = tc::launch_gemm_tc<256, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  if constexpr (B_MN) {
+    if (N <= 64) r = tc::launch_gemm_tc<64, false, true, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else if (N <= 128 || (h->debug_flags & DBG_BN128)) r = tc::launch_gemm_tc<128, false, true, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else r = tc::launch_gemm_tc<256, false, true, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  } else {
+    if (N <= 16) r = tc::launch_gemm_tc<16, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else if (N <= 32) r = tc::launch_gemm_tc<32, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else if (N <= 64) r = tc::launch_gemm_tc<64, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else if (N <= 128 || (h->debug_flags & DBG_BN128)) r = tc::launch_gemm_tc<128, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+    else r = tc::launch_gemm_tc<256, false, false, Epi>(A, B, A2, B2, M, N, 1, epi, st);
+  }
   if (r == 0) GM_LAUNCHED(h, st, PC_TC_GEMM);
   return r;
 }
@@ -542,15 +551,17 @@ static int lin_fwd(gmvae_handle* h, const TA* A, int64_t lda, int M, const LinVi
                    const TA* A2 = nullptr, int64_t lda2 = 0, const LinView* L2 = nullptr) {
   if constexpr (ALLOW_TC && std::is_same<TA, bf16>::value) {
     bool ok = tc_ok_fwd<TA>(h, A, lda, L);
-    if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->wt_bf16);
+    if (L2) ok = ok && lda2 % 8 == 0 && aligned16(A2) && aligned16(L2->w_bf16);
     if (ok) {
       // K extents are rounded up to the (zero-filled) 16-byte padding of the buffers.
-      tc::Operand a{A, lda, M, kpad(L.in, lda)}, b{L.wt_bf16, L.ld_wt, L.out, kpad(L.in, L.ld_wt)};
+      // B = W[in, out] as stored (row-major, the contraction index is the row): an MN-major operand.  Rows of W
+      // beyond `in` are outside the tensor map (read as zero); A's zero padding covers the rounded-up K extent.
+      tc::Operand a{A, lda, M, kpad(L.in, lda)}, b{L.w_bf16, L.ld_w, L.out, L.in};
       if (L2) {
-        tc::Operand a2{A2, lda2, M, kpad(L2->in, lda2)}, b2{L2->wt_bf16, L2->ld_wt, L2->out, kpad(L2->in, L2->ld_wt)};
-        return tc_dispatch_kk(h, a, b, &a2, &b2, M, L.out, epi, st);
+        tc::Operand a2{A2, lda2, M, kpad(L2->in, lda2)}, b2{L2->w_bf16, L2->ld_w, L2->out, L2->in};
+        return tc_dispatch_kk<Epi, true>(h, a, b, &a2, &b2, M, L.out, epi, st);
       }
-      return tc_dispatch_kk(h, a, b, nullptr, nullptr, M, L.out, epi, st);
+      return tc_dispatch_kk<Epi, true>(h, a, b, nullptr, nullptr, M, L.out, epi, st);
     }
   }
   GM_REQUIRE(L2 == nullptr, "two-segment forward requires the tensor-core path");
@@ -633,7 +644,7 @@ static int bias_grad(gmvae_handle* h, const T* dY, int64_t ldy, int M, int N, fl
 // TMA requirement); the padding columns are never written and stay zero from allocation.
 static inline int ldp(int n) { return round_up(n, 8); }
 
-template <typename A> struct MlpBufs { std::vector<A*> hid, dhid; };
+template <typename A> struct MlpBufs { std::vector<A*> hid, dhid; std::vector<uint32_t*> bits; };
 
 template <typename A>
 static MlpBufs<A> mlp_bufs(const gmvae_handle* h, const Mlp& m) {
@@ -641,6 +652,7 @@ static MlpBufs<A> mlp_bufs(const gmvae_handle* h, const Mlp& m) {
   for (size_t i = 0; i + 1 < m.layers.size(); ++i) {
     b.hid.push_back(h->buf<A>(m.name + ".h" + std::to_string(i)));
     b.dhid.push_back(h->buf<A>(m.name + ".dh" + std::to_string(i)));
+    b.bits.push_back(h->buf<uint32_t>(m.name + ".bits" + std::to_string(i)));
   }
   return b;
 }
@@ -656,7 +668,9 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
     int64_t ld = i == 0 ? ld0 : ldp(m.layers[i - 1].out);
     LinView L = view(h, m.layers[i], 0, i == 0 ? in0_cols : -1);
     EpiStore<A> epi{b.hid[i], (int64_t)ldp(m.layers[i].out), L.b, nullptr, 0, 1, 1.f};
+    if (h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = b.bits[i]; epi.ld_bits = round_up(M, 32); }
     GM_TRY(lin_fwd<A>(h, in, ld, M, L, epi, st));
+    h->relu_bits_valid[b.hid[i]] = epi.relu_bits != nullptr && h->last_gemm_chained;
   }
   return 0;
 }
@@ -692,6 +706,10 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
       const bool ok = top ? tc_ok_dgrad<TD>(h, dOut, ld_dout, Lf) : tc_ok_dgrad<A>(h, dA, ldd, Lf);
       float* cs = (fuse && i - 1 >= min_layer && ok) ? h->grads + m.layers[i - 1].b_off : nullptr;
       EpiReluMask<A, A> epi{b.dhid[i - 1], ldh, b.hid[i - 1], ldh, cs};
+      {
+        auto it = h->relu_bits_valid.find(b.hid[i - 1]);
+        if (h->chain_on && it != h->relu_bits_valid.end() && it->second) { epi.relu_bits = b.bits[i - 1]; epi.ld_bits = round_up(M, 32); }
+      }
       if (top) GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
       else GM_TRY((lin_dgrad<A>(h, dA, ldd, M, Lf, epi, st)));
       next_bias_done = cs != nullptr;
@@ -722,18 +740,26 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
   A* x_act = h->buf<A>("x_act");
   {
     const int64_t n = (int64_t)B * D;
-    // first kernel of the step: follows a memset node, launched with a full dependency
-    if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
-    else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp));
-    GM_LAUNCHED(h, st, PC_MISC);
-  }
-  if (!eps || (gm && !u)) {
+    const bool need_noise = !eps || (gm && !u);
     float* e = h->buf<float>("eps"); float* uu = gm ? h->buf<float>("u") : nullptr;
-    int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
-    int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
-    GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, uu, nu,
-                           (const DeviceState*)h->state, (uint64_t)h->rank));
-    GM_LAUNCHED(h, st, PC_MISC);
+    const int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
+    const int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
+    // first kernel of the step: follows a memset node, launched with a full dependency
+    if (D % 16 == 0 && need_noise) {      // image conversion and noise in one launch
+      const unsigned xb = (unsigned)((n / 16 + 255) / 256), nb = (unsigned)((q + 255) / 256);
+      GM_CHECK_CUDA(launch_k(prologue_kernel<A>, dim3(xb + nb), dim3(256), 0, st, false, x_u8, x_act, n, (int)xb, e, ne, uu, nu,
+                             (const DeviceState*)h->state, (uint64_t)h->rank));
+      GM_LAUNCHED(h, st, PC_MISC);
+    } else {
+      if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
+      else GM_CHECK_CUDA(launch_k(convert_x_rows_kernel<A>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, B, D, Dp));
+      GM_LAUNCHED(h, st, PC_MISC);
+      if (need_noise) {
+        GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, uu, nu,
+                               (const DeviceState*)h->state, (uint64_t)h->rank));
+        GM_LAUNCHED(h, st, PC_MISC);
+      }
+    }
     if (!eps) eps = e;
     if (gm && !u) u = uu;
   }
@@ -778,7 +804,9 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
       } else {
         EpiStore<A> epi{enc.hid[0], hid_ld(0), Lx.b, nullptr, 0, 1, 1.f};
+        if (h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = enc.bits[0]; epi.ld_bits = round_up(B, 32); }
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
+        h->relu_bits_valid[enc.hid[0]] = epi.relu_bits != nullptr && h->last_gemm_chained;
       }
     } else {   // fp32 validation mode: pre = y W[D:] + b, then relu(x W[:D] + pre)   (CUDA-core GEMMs)
       float* pre = h->buf<float>("pre_y");
@@ -812,6 +840,7 @@ template <typename A>
 static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
                                  const float* u_in, cudaStream_t st) {
   h->chain.njobs = 0; h->chain_tiles = 0; h->chain_writers.clear(); h->chain_counter_next = 0; h->chain_launch_idx = 0;
+  h->relu_bits_valid.clear();
   h->chain_counters = h->buf<int>("chain.counters");
   h->chain_on = std::is_same<A, bf16>::value && h->bf16_mode() && h->chain_counters && !(h->debug_flags & (DBG_NO_TC | DBG_NO_CHAIN));
   if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
@@ -1134,12 +1163,12 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
   return 0;
 }
 
-static int refresh_shadows(gmvae_handle* h, bool bump, cudaStream_t st) {
+// bf16 operand copies of every weight matrix after the parameters were written from outside
+// (initialisation, checkpoint restore).  During training the Adam kernel keeps them current itself.
+static int refresh_shadows(gmvae_handle* h, cudaStream_t st) {
   if (h->shadow_tiles > 0) {
     GM_CHECK_CUDA(launch_k(refresh_shadows_kernel, dim3(h->shadow_tiles), dim3(32, 8), 0, st, true, (const ShadowEntry*)h->shadow_dev,
-                           (int)h->shadow_host.size(), h->state, bump ? 1 : 0)); GM_LAUNCHED(h, st, PC_ADAM);
-  } else if (bump) {
-    GM_CHECK_CUDA(launch_k(bump_step_kernel, dim3(1), dim3(1), 0, st, true, h->state)); GM_LAUNCHED(h, st, PC_ADAM);
+                           (int)h->shadow_host.size())); GM_LAUNCHED(h, st, PC_ADAM);
   }
   return 0;
 }
@@ -1189,7 +1218,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   g_use_pdl = !(h->debug_flags & DBG_NO_PDL);
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
-  DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull;
+  DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull; s0.adam_blocks = 0; s0.pad = 0;
   GM_CHECK_CUDA(cudaMemcpy(h->state, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   *out = h;
   return 0;
@@ -1231,16 +1260,19 @@ int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, floa
     for (Mlp* m : mlps)
       for (auto& l : m->layers) {
         l.w_bf16 = h->buf<bf16>("shadow.w." + std::to_string(l.w_off));
-        l.wt_bf16 = h->buf<bf16>("shadow.wt." + std::to_string(l.w_off));
         ShadowEntry e;
-        e.w = params + l.w_off; e.w_bf16 = l.w_bf16; e.wt_bf16 = l.wt_bf16;
-        e.rows = l.in; e.cols = l.out; e.ld_w = l.ld_w; e.ld_wt = l.ld_wt;
-        e.tiles_x = (std::max(l.out, l.ld_w) + 31) / 32;
-        int tiles_y = (std::max(l.in, l.ld_wt) + 31) / 32;
+        e.w = params + l.w_off; e.w_bf16 = l.w_bf16;
+        e.off = l.w_off; e.rows = l.in; e.cols = l.out; e.ld_w = l.ld_w;
+        e.tiles_x = (l.ld_w + 31) / 32;
+        int tiles_y = (l.in + 31) / 32;
         e.tile_begin = h->shadow_tiles;
         h->shadow_tiles += e.tiles_x * tiles_y;
         h->shadow_host.push_back(e);
       }
+    // sorted by flat offset: the Adam kernel finds the matrix an element belongs to by bisection
+    std::sort(h->shadow_host.begin(), h->shadow_host.end(), [](const ShadowEntry& a, const ShadowEntry& b) { return a.off < b.off; });
+    h->shadow_tiles = 0;
+    for (auto& e : h->shadow_host) { e.tile_begin = h->shadow_tiles; h->shadow_tiles += e.tiles_x * ((e.rows + 31) / 32); }
     if (h->shadow_dev) cudaFree(h->shadow_dev);
     GM_CHECK_CUDA(cudaMalloc(&h->shadow_dev, sizeof(ShadowEntry) * h->shadow_host.size()));
     GM_CHECK_CUDA(cudaMemcpy(h->shadow_dev, h->shadow_host.data(), sizeof(ShadowEntry) * h->shadow_host.size(), cudaMemcpyHostToDevice));
@@ -1250,7 +1282,7 @@ int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, floa
 
 int gmvae_params_updated(gmvae_handle* h, void* stream) {
   GM_TRY(check_ready(h));
-  return refresh_shadows(h, false, (cudaStream_t)stream);
+  return refresh_shadows(h, (cudaStream_t)stream);
 }
 
 int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
@@ -1281,11 +1313,13 @@ static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st) {
   int64_t n = h->n_params;
   // after a cross-stream join (data-parallel all-reduce) the kernel is launched with a full dependency
   const bool pdl = !(h->comm && h->world > 1);
+  // one launch: parameter update, the bf16 operand copies of the weight matrices, global_step += 1
   GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n / 4 + 255) / 256 + 1)), dim3(256), 0, st, pdl, h->params, (const float*)h->grads,
-                         h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, (const DeviceState*)h->state,
-                         (const float*)(h->grads + h->n_params), loss_terms));
+                         h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, h->state,
+                         (const float*)(h->grads + h->n_params), loss_terms, (const ShadowEntry*)h->shadow_dev,
+                         h->bf16_mode() ? (int)h->shadow_host.size() : 0));
   GM_LAUNCHED(h, st, PC_ADAM);
-  return refresh_shadows(h, true, st);
+  return 0;
 }
 
 int gmvae_adam_step(gmvae_handle* h, void* stream) {

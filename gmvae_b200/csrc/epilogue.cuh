@@ -354,6 +354,8 @@ struct EpiStore {
   int relu;                 // 0 none, 1 ReLU, 2 sigmoid (Bernoulli mean of the decoder, inference only)
   float scale;
   float shift;              // constant added with the bias (gen_bias_init); 0 when omitted from the initialiser
+  uint32_t* relu_bits;      // chained kernel only: [N/32, ld_bits >= M] words, bit (31 - j) of word [w][m] = (out[m, 32 w + j] > 0); or null
+  int ld_bits;
 
   template <int NV> struct Pre { float b[NV >= 16 ? 1 : NV]; float a[(MODE != EPI_PLAIN) ? NV : 1]; };
 
@@ -520,6 +522,8 @@ struct EpiReluMask {
   OutT* out; int64_t ld;
   const HT* h; int64_t ldh;
   float* colsum;            // fused bias gradient of the layer below (tensor-core path only) or null
+  const uint32_t* relu_bits;  // chained kernel only: the 1-bit form of [h > 0] written by the forward job (EpiStore::relu_bits), or null
+  int ld_bits;
 
   template <int NV> struct Pre {
     float h[staged_io<HT, NV>::value ? 1 : NV];

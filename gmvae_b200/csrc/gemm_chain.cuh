@@ -249,14 +249,23 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
         const int gcol = g * gw * CW;                        // first column of the group within the tile
         // the previous bulk store issued from this patch must have read it before it is overwritten
         if (lane == 0) bulk_wait_read0();
-        if constexpr (KIND == EK_RELUMASK) fence_proxy_async();   // this warp's earlier generic reads of the patch precede the TMA write
+        uint32_t hbits = 0;
+        bool use_bits = false;
+        if constexpr (KIND == EK_RELUMASK) {
+          use_bits = epi.relu_bits != nullptr;
+          if (!use_bits) fence_proxy_async();   // this warp's earlier generic reads of the patch precede the TMA write
+        }
         __syncwarp();
         if constexpr (KIND == EK_RELUMASK) {
-          if (lane == 0) {
+          if (use_bits) {
+            // 32 mask bits of this lane's row for the group's 32 columns (written by the forward job of this layer)
+            if (mvalid) hbits = __ldcg(epi.relu_bits + (int64_t)((n0 + gcol) >> 5) * epi.ld_bits + m);   // L2: written by another SM in this launch
+          } else if (lane == 0) {
             mbar_expect_tx(op_bar, (uint32_t)CHAIN_PATCH_BYTES);
             tma_load_2d(&J.c, op_bar, S.patches + e * CHAIN_PATCH_BYTES, n0 + gcol, mrow0);
           }
         }
+        uint32_t obits = 0; int obits_chunks = 0;
         uint4 xq[2];
         if constexpr (KIND == EK_BCE) {
           // image bytes of this lane's row (16 per chunk), fetched ahead of the accumulator
@@ -277,8 +286,10 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
         }
         wait_acc();
         if constexpr (KIND == EK_RELUMASK) {
-          mbar_wait(op_bar, op_phase);
-          op_phase ^= 1;
+          if (!use_bits) {
+            mbar_wait(op_bar, op_phase);
+            op_phase ^= 1;
+          }
         }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -294,7 +305,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
             }
             uint4 h0, h1;
             if constexpr (KIND == EK_RELUMASK) {
-              h0 = lds128(patch_unit<64>(patch, lane, 2 * c)); h1 = lds128(patch_unit<64>(patch, lane, 2 * c + 1));
+              if (!use_bits) { h0 = lds128(patch_unit<64>(patch, lane, 2 * c)); h1 = lds128(patch_unit<64>(patch, lane, 2 * c + 1)); }
             }
             tmem_ld16_wait(r);
             float v[CW];
@@ -314,7 +325,18 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
                   if (epi.relu == 1) v[i] = fmaxf(v[i], 0.f);
                   else if (epi.relu == 2) v[i] = sigmoid_f(v[i] + epi.shift);
                 }
+                if (epi.relu_bits) {
+                  // [v == 0] for v >= +0 is the top bit of bits(v) - 1; one funnel shift per element appends it
+                  // (element e of the group ends at bit 31 - e; complemented when the word is stored)
+#pragma unroll
+                  for (int i = 0; i < CW; ++i) obits = __funnelshift_l(__float_as_uint(v[i]) - 1u, obits, 1);
+                  ++obits_chunks;
+                }
               } else if constexpr (KIND == EK_RELUMASK) {
+               if (use_bits) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i) v[i] = ((hbits >> (31 - (c * CW + i))) & 1u) ? v[i] : 0.f;
+               } else {
                 const __nv_bfloat162* ph0 = reinterpret_cast<const __nv_bfloat162*>(&h0);
                 const __nv_bfloat162* ph1 = reinterpret_cast<const __nv_bfloat162*>(&h1);
 #pragma unroll
@@ -323,6 +345,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
                   v[2 * k] = a.x > 0.f ? v[2 * k] : 0.f; v[2 * k + 1] = a.y > 0.f ? v[2 * k + 1] : 0.f;
                   v[8 + 2 * k] = b.x > 0.f ? v[8 + 2 * k] : 0.f; v[8 + 2 * k + 1] = b.y > 0.f ? v[8 + 2 * k + 1] : 0.f;
                 }
+               }
               } else if constexpr (KIND == EK_BCE) {
                 const uint8_t* xb = reinterpret_cast<const uint8_t*>(&xq[c]);
                 const int nvalid = min(CW, N - (n0 + ci * CW));
@@ -347,6 +370,12 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
               pack16(v, lo, hi);
               sts128(patch_unit<64>(patch, lane, 2 * c), lo); sts128(patch_unit<64>(patch, lane, 2 * c + 1), hi);
             }
+          }
+        }
+        if constexpr (KIND == EK_STORE_BF16) {
+          if (epi.relu_bits && mvalid) {
+            if (obits_chunks < 2) obits = (obits << 16) | 0xFFFFu;     // the group's second chunk lies beyond N
+            epi.relu_bits[(int64_t)((n0 + gcol) >> 5) * epi.ld_bits + m] = ~obits;   // a warp's 32 rows: one 128-byte line
           }
         }
         fence_proxy_async();                                  // generic-proxy writes to the patch -> visible to the bulk store

@@ -8,17 +8,25 @@
 namespace gmvae {
 
 
+// bf16 GEMM-operand copy of one weight matrix
+struct ShadowEntry {
+  const float* w; bf16* w_bf16;
+  long long off;             // flat offset of the matrix in the parameter buffer
+  int rows, cols, ld_w;
+  int tiles_x, tile_begin;   // tiles along cols; first flat tile index of this entry
+};
+
 struct DeviceState {           // owned by the handle, lives on the device
   long long step;              // global_step (runners.py:171)
   unsigned long long seed;
+  unsigned int adam_blocks;    // blocks of the running Adam launch that have read `step` (the last one bumps it)
+  unsigned int pad;
 };
 
 // ---- x: bool bytes -> GEMM operand type (vae.py:75, gmvae.py:86,104: tf.cast(x, float32)) ----
 template <typename T>
-__global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n) {
-  griddep_wait();
-  griddep_launch();
-  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+__device__ __forceinline__ void convert_x_body(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n, int64_t block) {
+  int64_t i = (block * blockDim.x + threadIdx.x) * 16;
   if (i + 16 <= n) {
     uint4 t = *reinterpret_cast<const uint4*>(x + i);
     const uint8_t* p = reinterpret_cast<const uint8_t*>(&t);
@@ -32,6 +40,12 @@ __global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ 
   } else {
     for (int64_t j = i; j < n; ++j) out[j] = from_f32<T>((float)x[j]);
   }
+}
+template <typename T>
+__global__ void convert_x_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n) {
+  griddep_wait();
+  griddep_launch();
+  convert_x_body<T>(x, out, n, blockIdx.x);
 }
 
 // generic variant: rows of D bytes -> rows of ld elements (ld >= D; padding left untouched)
@@ -49,12 +63,10 @@ __global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restri
 // ---- noise (only when the caller does not inject it) -----------------------------------------
 // eps ~ N(0,1) (tf.random_normal inside MultivariateNormalDiag.sample), u ~ U(tiny,1)
 // (RelaxedOneHotCategorical.sample).  Keyed by (seed, step, stream id, element index).
-__global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
-                                  const DeviceState* st, uint64_t rank_stream) {
-  griddep_wait();
-  griddep_launch();
+__device__ __forceinline__ void fill_noise_body(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
+                                                const DeviceState* st, uint64_t rank_stream, int64_t block) {
   const uint64_t seed = st->seed, step = (uint64_t)st->step;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = block * blockDim.x + threadIdx.x;
   int64_t q_eps = (n_eps + 3) / 4, q_u = (n_u + 3) / 4;
   uint32_t r[4];
   if (i < q_eps) {
@@ -72,6 +84,21 @@ __global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float*
     for (int j = 0; j < 4; ++j)
       if (k * 4 + j < n_u) u[k * 4 + j] = u01(r[j]);
   }
+}
+__global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
+                                  const DeviceState* st, uint64_t rank_stream) {
+  griddep_wait();
+  griddep_launch();
+  fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, blockIdx.x);
+}
+// first launch of a training step: blocks [0, x_blocks) convert the image bytes, the rest draw the noise
+template <typename T>
+__global__ void prologue_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n, int x_blocks, float* __restrict__ eps,
+                                int64_t n_eps, float* __restrict__ u, int64_t n_u, const DeviceState* st, uint64_t rank_stream) {
+  griddep_wait();
+  griddep_launch();
+  if ((int)blockIdx.x < x_blocks) convert_x_body<T>(x, out, n, blockIdx.x);
+  else fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, (int64_t)blockIdx.x - x_blocks);
 }
 
 // ---- q(y|x) head, forward (gmvae.py:238-240, 262-263; utils.py:165-170) ------------------------
@@ -966,8 +993,9 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __res
 // lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // theta -= lr_t m / (sqrt(v) + eps).   t = step+1 read from the device; one flat pass.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr, float b1, float b2, float eps, const DeviceState* st,
-                            const float* __restrict__ acc, float* __restrict__ loss_out) {
+                            int64_t n, float lr, float b1, float b2, float eps, DeviceState* st,
+                            const float* __restrict__ acc, float* __restrict__ loss_out,
+                            const ShadowEntry* __restrict__ shadows, int n_shadows) {
   griddep_wait();
   griddep_launch();
   __shared__ float lr_t_s;
@@ -978,10 +1006,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   if (threadIdx.x == 0) {
     double t = (double)(st->step + 1);
     lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    // global_step += 1 once every block of this launch has read it: the last block to get here does it
+    __threadfence();
+    if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) { st->adam_blocks = 0; st->step += 1; }
   }
   __syncthreads();
   const float lr_t = lr_t_s;
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  // the weight matrix this group of 4 belongs to (tensors start on 16-byte boundaries, so a group never straddles two)
+  int lo = 0, hi = n_shadows;                               // first entry with off > i
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (shadows[mid].off <= i) lo = mid + 1; else hi = mid; }
+  bf16* wb = nullptr; int cols = 0, ld_w = 0; int64_t rel = 0, lim = 0;
+  if (lo > 0) {
+    const ShadowEntry& E = shadows[lo - 1];
+    rel = i - E.off; lim = (int64_t)E.rows * E.cols;
+    if (rel < lim) { wb = E.w_bf16; cols = E.cols; ld_w = E.ld_w; }
+  }
   if (i + 4 <= n) {
     float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
     float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
@@ -993,12 +1034,24 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       P[j] -= lr_t * Mm[j] / (sqrtf(V[j]) + eps);
     }
     *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+    if (wb) {                                               // bf16 GEMM operand copy [rows, ld_w] of the updated weights
+      if (cols == ld_w && rel + 4 <= lim) {
+        *reinterpret_cast<uint2*>(wb + rel) = make_uint2(pack_bf16x2(P[0], P[1]), pack_bf16x2(P[2], P[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t e = rel + j;
+          if (e < lim) wb[(e / cols) * ld_w + (e % cols)] = __float2bfloat16_rn(P[j]);
+        }
+      }
+    }
   } else {
     for (int64_t k = i; k < n; ++k) {
       float mk = b1 * m[k] + (1.f - b1) * g[k];
       float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
       m[k] = mk; v[k] = vk;
       p[k] -= lr_t * mk / (sqrtf(vk) + eps);
+      if (wb) { const int64_t e = rel + (k - i); if (e < lim) wb[(e / cols) * ld_w + (e % cols)] = __float2bfloat16_rn(p[k]); }
     }
   }
 }
@@ -1007,16 +1060,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // For W [rows=in, cols=out] fp32: w_bf16 [in, ld_w] (dgrad B operand, K-major over `out`) and
 // wt_bf16 [out, ld_wt] (forward B operand, K-major over `in`).  One entry per matrix; a 32x32
 // tile per block, transposed through shared memory.  Block (0,0,0) also advances global_step.
-struct ShadowEntry {
-  const float* w; bf16* w_bf16; bf16* wt_bf16;
-  int rows, cols, ld_w, ld_wt;
-  int tiles_x, tile_begin;   // tiles along cols; first flat tile index of this entry
-};
-__global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, int n_entries, DeviceState* st, int bump_step) {
+__global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, int n_entries) {
   griddep_wait();
   griddep_launch();
-  __shared__ float tile[32][33];
-  if (bump_step && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) st->step += 1;
   int e = 0;
   while (e + 1 < n_entries && (int)blockIdx.x >= entries[e + 1].tile_begin) ++e;
   const ShadowEntry E = entries[e];
@@ -1025,15 +1071,7 @@ __global__ void refresh_shadows_kernel(const ShadowEntry* __restrict__ entries, 
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int r = r0 + i, c = c0 + threadIdx.x;
     float v = (r < E.rows && c < E.cols) ? E.w[(int64_t)r * E.cols + c] : 0.f;
-    tile[i][threadIdx.x] = v;
-    if (E.w_bf16 && r < E.rows && c < E.ld_w) E.w_bf16[(int64_t)r * E.ld_w + c] = __float2bfloat16_rn(v);
-  }
-  __syncthreads();
-  if (E.wt_bf16) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      int c = c0 + i, r = r0 + threadIdx.x;  // output row = c (an `out` index), output col = r (an `in` index)
-      if (c < E.cols && r < E.ld_wt) E.wt_bf16[(int64_t)c * E.ld_wt + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-    }
+    if (r < E.rows && c < E.ld_w) E.w_bf16[(int64_t)r * E.ld_w + c] = __float2bfloat16_rn(v);
   }
 }
 __global__ void bump_step_kernel(DeviceState* st) {
