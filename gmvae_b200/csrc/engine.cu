@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -120,7 +121,7 @@ struct LinView {
 };
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
-       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512,
+       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512, DBG_NO_ROW_JOBS = 1024, DBG_NO_SPREAD = 4096,
        DBG_RELU_BITS = 2048 /* 1-bit ReLU masks between the chained forward and backward jobs: measured 1 % slower than
                                reading the bf16 activation through TMA, kept as an experiment */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
@@ -398,7 +399,7 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain_launch_idx++;
   const int grid = std::min(h->chain_tiles, tc::num_sms());
   GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
-  h->chain.njobs = 0; h->chain_tiles = 0; h->chain_writers.clear();
+  h->chain.njobs = 0; h->chain.nmaps = 0; h->chain_tiles = 0; h->chain_writers.clear();
   h->launches++;
   if (h->profiling) GM_TRY(profile_mark(h, st, 0 /*PC_TC_GEMM*/));
   if (h->debug_flags & DBG_SYNC_EACH) GM_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -441,7 +442,8 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M, tiles_n = (N + block_n - 1) / block_n;
   // ---- dependencies
   const void* reads[4] = {A1.ptr, A2 ? A2->ptr : nullptr, a_mn ? (const void*)B1.ptr : nullptr, epi.read_ptr()};
-  tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0, epi_dep = -1; bool need_flush = h->chain.njobs >= tc::CHAIN_MAX_JOBS;
+  tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0, epi_dep = -1;
+  bool need_flush = h->chain.njobs >= tc::CHAIN_MAX_JOBS || h->chain.nmaps + 6 > tc::CHAIN_MAX_MAPS;
   for (int i = 0; i < 4 && !need_flush; ++i) {
     const char* p = reinterpret_cast<const char*>(reads[i]);
     if (!p) continue;
@@ -453,19 +455,24 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
       for (int d = 0; d < ndeps; ++d) if (deps[d].base == P.sig_base) dup = d;
       if (dup >= 0) {
         if (i == 3) { if (deps[dup].by_k) { need_flush = true; break; } epi_dep = dup; }
+        if (i != 1) deps[dup].seg2 = 0;
         continue;
       }
       if (ndeps == tc::CHAIN_MAX_DEPS) { need_flush = true; break; }
       if (i == 3) epi_dep = ndeps;
       // by_k: this operand's rows are the contraction dimension (weight gradient over the batch)
       const bool by_k = a_mn && i != 3;
-      deps[ndeps++] = tc::ChainDep{P.sig_base, tc::EPI_WARPS * P.tiles_n * P.num_splits, by_k ? 1 : 0, (P.M + tc::BLOCK_M - 1) / tc::BLOCK_M};
+      // an operand of the second K segment only (i == 1, K-major jobs): its rows are needed when that segment starts
+      deps[ndeps++] = tc::ChainDep{P.sig_base, tc::EPI_WARPS * P.tiles_n * P.num_splits, by_k ? 1 : 0, (P.M + tc::BLOCK_M - 1) / tc::BLOCK_M,
+                                   (i == 1 && !a_mn) ? 1 : 0};
     }
   }
   if (need_flush) { GM_TRY(chain_flush(h, st)); ndeps = 0; epi_dep = -1; }
   // ---- the job
   tc::ChainJob& J = h->chain.jobs[h->chain.njobs];
-  auto mk = [&](CUtensorMap* m, const tc::Operand& o, bool mn, int box_rows) -> int {
+  auto mk = [&](int* idx, const tc::Operand& o, bool mn, int box_rows) -> int {
+    CUtensorMap* m = &h->chain.maps[h->chain.nmaps];
+    *idx = h->chain.nmaps++;
     if (mn) return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.rows, (uint64_t)o.k, (uint64_t)o.ld, 64, tc::BLOCK_K);
     return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.k, (uint64_t)o.rows, (uint64_t)o.ld, tc::BLOCK_K, (uint32_t)box_rows);
   };
@@ -504,14 +511,62 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   J.gw = 0; J.c = J.a1; J.d = J.a1;
   if (io.out) {
     J.gw = io.elem == 2 ? 2 : 1;
-    GM_TRY(tc::make_tmap(&J.d, io.out, io.elem, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld, io.elem == 2 ? 32 : 16, 32, 64));
-    if (io.opnd) GM_TRY(tc::make_tmap(&J.c, io.opnd, 2, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld_opnd, 32, 32, 64));
+    J.d = h->chain.nmaps++;
+    GM_TRY(tc::make_tmap(&h->chain.maps[J.d], io.out, io.elem, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld, io.elem == 2 ? 32 : 16, 32, 64));
+    if (io.opnd) {
+      J.c = h->chain.nmaps++;
+      GM_TRY(tc::make_tmap(&h->chain.maps[J.c], io.opnd, 2, (uint64_t)N, (uint64_t)M, (uint64_t)io.ld_opnd, 32, 32, 64));
+    }
   }
   memset(J.epi, 0, sizeof(J.epi));
   memcpy(J.epi, &epi, sizeof(Epi));
   h->chain_tiles += J.total_tiles;
   h->chain.njobs++;
   h->last_gemm_chained = true;
+  if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
+  return 0;
+}
+// Appends a row job (a distribution head run by the epilogue warps on 128-row blocks) to the chain.
+// `reads`: buffers whose rows it consumes; `writes`: {pointer, bytes} of every buffer it produces.
+template <class P>
+static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::initializer_list<const void*> reads,
+                          std::initializer_list<std::pair<const void*, size_t>> writes, cudaStream_t st) {
+  static_assert(sizeof(P) <= tc::CHAIN_EPI_BYTES, "row-job parameters do not fit the job record");
+  const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0;
+  bool need_flush = h->chain.njobs >= tc::CHAIN_MAX_JOBS;
+  for (const void* r : reads) {
+    const char* p = reinterpret_cast<const char*>(r);
+    if (!p || need_flush) continue;
+    for (const auto& w : h->chain_writers) {
+      if (p < w.lo || p >= w.hi) continue;
+      const tc::ChainJob& Pj = h->chain.jobs[w.job];
+      if (p != w.lo || Pj.sig_base < 0) { need_flush = true; break; }
+      bool dup = false;
+      for (int d = 0; d < ndeps; ++d) dup = dup || deps[d].base == Pj.sig_base;
+      if (dup) continue;
+      if (ndeps == tc::CHAIN_MAX_DEPS) { need_flush = true; break; }
+      deps[ndeps++] = tc::ChainDep{Pj.sig_base, tc::EPI_WARPS * Pj.tiles_n * Pj.num_splits, 0, (Pj.M + tc::BLOCK_M - 1) / tc::BLOCK_M, 0};
+    }
+  }
+  if (need_flush) { GM_TRY(chain_flush(h, st)); ndeps = 0; }
+  tc::ChainJob& J = h->chain.jobs[h->chain.njobs];
+  memset(&J, 0, sizeof(J));
+  J.M = M; J.N = 0; J.kind = kind; J.num_splits = 1;
+  J.tiles_n = 1; J.tiles_mn = tiles_m; J.total_tiles = tiles_m; J.tile_base = h->chain_tiles;
+  J.ndeps = ndeps; J.epi_dep = -1;
+  for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
+  J.sig_base = -1;
+  if (h->chain_counter_next + tiles_m <= h->chain_counter_cap) {
+    J.sig_base = h->chain_counter_next; h->chain_counter_next += tiles_m;
+  } else {
+    h->chain_flush_after = true;
+  }
+  for (const auto& w : writes)
+    if (w.first) h->chain_writers.push_back({reinterpret_cast<const char*>(w.first), reinterpret_cast<const char*>(w.first) + w.second, h->chain.njobs});
+  memcpy(J.epi, &prm, sizeof(P));
+  h->chain_tiles += J.total_tiles;
+  h->chain.njobs++;
   if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
   return 0;
 }
@@ -525,7 +580,7 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
     if (h->chain_on && chain_io(epi).ok) {
       // outputs staged for TMA stores use tiles that are whole 32-column groups; MN-major B comes in 64-column slabs
       const bool f32 = tc::epi_kind<Epi>::value == tc::EK_STORE_F32;
-      const int bn = (!B_MN && f32 && N <= 16) ? 16 : (!B_MN && f32 && N <= 32) ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+      const int bn = (!B_MN && f32 && N <= 16) ? 16 : (!B_MN && f32 && N <= 32) ? 32 : N <= 64 ? 64 : (N <= 128 || (h->debug_flags & DBG_BN128)) ? 128 : 256;
       return chain_add(h, A, B, A2, B2, M, N, bn, false, B_MN, 1, epi, st);
     }
   }
@@ -683,7 +738,11 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
 // is the bias gradient of layer i-1 (no separate pass over dh).
 template <typename A, typename TD>
 static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols,
-                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false, int min_layer = 0) {
+                        const TD* dOut, int64_t ld_dout, int M, cudaStream_t st, bool dout_bias_done = false, int min_layer = 0,
+                        std::vector<std::function<int()>>* defer = nullptr, int defer_below = 0) {
+  // `defer`: the weight-gradient GEMMs of layers < defer_below (off the critical path of the backward pass) are not
+  // issued here but returned, upper layer first, so that the caller can place them where the chain of dependent
+  // jobs needs filler work.
   const int nl = (int)m.layers.size();
   const bool fuse = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
   bool bias_done = dout_bias_done;   // bias gradient of the layer whose output gradient we hold
@@ -714,13 +773,23 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
       else GM_TRY((lin_dgrad<A>(h, dA, ldd, M, Lf, epi, st)));
       next_bias_done = cs != nullptr;
     }
+    const bool need_bias = !bias_done;
+    const int out_cols = l.out;
+    std::function<int()> wg;
     if (top) {
-      GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
-      if (!bias_done) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, l.out, L.db, st));
+      wg = [=]() -> int {
+        GM_TRY((lin_wgrad<A, TD>(h, in, ld, dOut, ld_dout, M, L, st)));
+        if (need_bias) GM_TRY(bias_grad<TD>(h, dOut, ld_dout, M, out_cols, L.db, st));
+        return 0;
+      };
     } else {
-      GM_TRY((lin_wgrad<A, A>(h, in, ld, dA, ldd, M, L, st)));
-      if (!bias_done) GM_TRY(bias_grad<A>(h, dA, ldd, M, l.out, L.db, st));
+      wg = [=]() -> int {
+        GM_TRY((lin_wgrad<A, A>(h, in, ld, dA, ldd, M, L, st)));
+        if (need_bias) GM_TRY(bias_grad<A>(h, dA, ldd, M, out_cols, L.db, st));
+        return 0;
+      };
     }
+    if (defer && i < defer_below) defer->push_back(wg); else GM_TRY(wg());
     bias_done = next_bias_done;
   }
   return 0;
@@ -779,6 +848,13 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
+    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS);
+    if (rows_ok && K <= 16 && Kp <= 16 && u) {
+      // q(y|x) head as a job of the chain: no launch, no pipeline drain between encoder_y and encoder_gmm
+      tc::RowsYFwd prm{logits_y, u, K, 1.f / c.temperature, inv_bg, y_f32, reinterpret_cast<bf16*>(y_act), Kp, acc};
+      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Y_FWD, prm, B, {logits_y, u},
+                            {{y_f32, (size_t)B * K * 4}, {y_act, (size_t)B * Kp * 2}}, st));
+    } else {
     GM_TRY(chain_flush(h, st));
     if (std::is_same<A, bf16>::value && K <= 16 && Kp <= 16) {
       GM_CHECK_CUDA(launch_k(head_y_fwd_row_kernel, dim3((B + 127) / 128), dim3(128), 0, st, true, (const float*)logits_y, u, B, K,
@@ -788,11 +864,6 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
                              1.f / c.temperature, inv_bg, y_f32, y_act, Kp, acc));
     }
     GM_LAUNCHED(h, st, PC_HEADS);
-    // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327)
-    {
-      const Linear& l = h->prior_gmm.layers[0];
-      EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 1.f};
-      GM_TRY(lin_fwd<A>(h, y_act, Kp, B, view(h, l), epi, st));
     }
     // q(z|x,y) layer 0: [x,y] W = x W[:D] + y W[D:]  (no concat, base.py:66)
     LinView Lx = view(h, enc_l0, 0, D), Ly = view(h, enc_l0, D, K);
@@ -820,6 +891,13 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
         GM_TRY((lin_fwd<A, EpiStore<A, EPI_ADDEND>, false>(h, x_act, Dp, B, Lx, epi, st)));
       }
     }
+    // p(z|y): one linear K -> 2Z (gmvae.py:243, 321-327).  Issued after encoder_gmm's first layer: in the chained kernel that
+    // layer starts on its x segment while the y head is still finishing, and y is complete by the time this thin job runs.
+    {
+      const Linear& l = h->prior_gmm.layers[0];
+      EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 1.f};
+      GM_TRY(lin_fwd<A>(h, y_act, Kp, B, view(h, l), epi, st));
+    }
     GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, B, 1, st));
   } else {
     GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, B, 0, st));
@@ -839,14 +917,14 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
 template <typename A>
 static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, int Bg, const float* eps_in,
                                  const float* u_in, cudaStream_t st) {
-  h->chain.njobs = 0; h->chain_tiles = 0; h->chain_writers.clear(); h->chain_counter_next = 0; h->chain_launch_idx = 0;
+  h->chain.njobs = 0; h->chain.nmaps = 0; h->chain_tiles = 0; h->chain_writers.clear(); h->chain_counter_next = 0; h->chain_launch_idx = 0;
   h->relu_bits_valid.clear();
   h->chain_counters = h->buf<int>("chain.counters");
   h->chain_on = std::is_same<A, bf16>::value && h->bf16_mode() && h->chain_counters && !(h->debug_flags & (DBG_NO_TC | DBG_NO_CHAIN));
   if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
   int r = forward_backward_body<A>(h, x_u8, B, Bg, eps_in, u_in, st);
   if (r == 0) r = chain_flush(h, st);
-  h->chain_on = false; h->chain.njobs = 0;
+  h->chain_on = false; h->chain.njobs = 0; h->chain.nmaps = 0;
   return r;
 }
 
@@ -887,9 +965,14 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   float* z_f32 = h->buf<float>("z_f32");
   {
     int64_t n = (int64_t)B * Z;
-    GM_TRY(chain_flush(h, st));
     const bool v4 = std::is_same<A, bf16>::value && Z % 4 == 0 && Z <= 256 && aligned16(eps) && aligned16(enc_out) &&
                     (prior_mode != 2 || aligned16(prior_out));
+    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && v4 && prior_mode != 1 && z_f32 == nullptr;
+    if (rows_ok) {
+      tc::RowsZFwd prm{enc_out, eps, prior_out, prior_mode, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, reinterpret_cast<bf16*>(z_act), Zp, acc};
+      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_FWD, prm, B, {enc_out, eps, prior_out}, {{z_act, (size_t)B * Zp * 2}}, st));
+    } else {
+    GM_TRY(chain_flush(h, st));
     if (v4) {
       const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256, 8 * tc::num_sms());
       GM_CHECK_CUDA(launch_k(head_z_fwd_v4_kernel, dim3(blocks), dim3(256), 0, st, true, (const float*)enc_out, eps, (const float*)prior_out,
@@ -899,6 +982,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
                              (const float*)prior_out, prior_mode, B, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, z_act, Zp, z_f32, acc));
     }
     GM_LAUNCHED(h, st, PC_HEADS);
+    }
   }
   float* dz_prior = h->buf<float>("dz_prior");
   if (prior_mode == 1) {
@@ -925,19 +1009,37 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   }
 
   // -------------------------------------------------------------------------- backward
-  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, B, st, dec_bias_fused)));
+  // Order of the jobs: the data gradients form the critical path (each depends on the one before); the weight
+  // gradients only read finished tensors, so in the chained kernel they are placed where that path has bubbles:
+  // right after the thin jobs (dz, dy, the heads), whose dependants would otherwise wait out a full tile latency.
+  const bool spread = h->chain_on && !(h->debug_flags & DBG_NO_SPREAD) && !(h->comm && h->world > 1 && h->overlap_comm);
+  std::vector<std::function<int()>> wg_dec;          // weight gradients of the two lowest decoder layers
+  GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, B, st, dec_bias_fused, 0, spread ? &wg_dec : nullptr,
+                             std::min(2, nl - 1))));
   {  // dz = d(first decoder layer input)
     const Linear& l0 = h->decoder.layers[0];
     EpiStore<float> epi{dz, (int64_t)Z, nullptr, nullptr, 0, 0, 1.f};
     if (nl == 1) GM_TRY((lin_dgrad<A>(h, dlogits_x, Dp, B, view(h, l0), epi, st)));
     else GM_TRY((lin_dgrad<A>(h, dec.dhid[0], hid_ld(0), B, view(h, l0), epi, st)));
   }
+  size_t wg_dec_next = 0;
+  if (wg_dec.size() > 1) GM_TRY(wg_dec[wg_dec_next++]());   // filler between dz and the z head that consumes it
   GM_TRY(comm_bucket(h, st, h->bucket_end[0]));     // decoder gradients are final
   A* d_prior_out = h->buf<A>("d_prior_out");
   bool enc_bias_fused = false;
   {
     int64_t n = (int64_t)B * Z;
     enc_bias_fused = Z <= 256 && !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && enc_bias_fused && prior_mode != 1 &&
+                         (Z == 4 || Z == 8 || Z == 16 || Z == 32 || Z == 64) && aligned16(eps) && aligned16(enc_out) && aligned16(dz) &&
+                         (prior_mode != 2 || aligned16(prior_out));
+    if (rows_ok) {
+      tc::RowsZBwd prm{enc_out, eps, prior_out, dz, prior_mode, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, reinterpret_cast<bf16*>(d_enc_out),
+                       reinterpret_cast<bf16*>(d_prior_out), Z2p, h->grads + enc_last.b_off,
+                       gm ? h->grads + h->prior_gmm.layers[0].b_off : (float*)nullptr};
+      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_BWD, prm, B, {dz, enc_out, prior_out, eps},
+                            {{d_enc_out, (size_t)B * Z2p * 2}, {gm ? d_prior_out : nullptr, (size_t)B * Z2p * 2}}, st));
+    } else {
     GM_TRY(chain_flush(h, st));
     const bool v4 = std::is_same<A, bf16>::value && enc_bias_fused && Z % 4 == 0 && aligned16(eps) && aligned16(enc_out) && aligned16(dz) &&
                     (prior_mode != 2 || aligned16(prior_out)) && (prior_mode != 1 || aligned16(dz_prior));
@@ -963,8 +1065,11 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
                              c.sigma_min, inv_bg, d_enc_out, d_prior_out, Z2p));
     }
     GM_LAUNCHED(h, st, PC_HEADS);
+    }
   }
-  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st, enc_bias_fused)));
+  for (; wg_dec_next < wg_dec.size(); ++wg_dec_next) GM_TRY(wg_dec[wg_dec_next]());   // filler between the z head and the encoder's data gradients
+  std::vector<std::function<int()>> wg_enc;          // weight gradient of the encoder's first layer (x part)
+  GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st, enc_bias_fused, 0, (spread && gm) ? &wg_enc : nullptr, 1)));
   if (gm) {
     float* dy = h->buf<float>("dy"); A* dlogits_y = h->buf<A>("dlogits_y");
     LinView Ly = view(h, enc_l0, D, K);
@@ -980,16 +1085,26 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
       if (dy_two_seg) GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st, d_prior_out, Z2p, &Lp)));
       else GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st)));
     }
-    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, dh0, ld_dh0, B, Ly, st)));
-    // prior_gmm: dWp = y^T d_prior_out ; dbp
-    GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
-    if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
     if (!dy_two_seg) {
       EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
       GM_TRY((lin_dgrad<A>(h, d_prior_out, Z2p, B, Lp, e, st)));
     }
+    for (auto& f : wg_enc) GM_TRY(f());               // dW[:D] = x^T dh0: filler between dy and the y head that consumes it
+    auto wg_y = [&]() -> int {
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, dh0, ld_dh0, B, Ly, st)));
+      // prior_gmm: dWp = y^T d_prior_out ; dbp
+      GM_TRY((lin_wgrad<A, A>(h, y_act, Kp, d_prior_out, Z2p, B, Lp, st)));
+      if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
+      return 0;
+    };
+    if (!spread) GM_TRY(wg_y());
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    if (h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && K <= 16 && Kp <= 16) {
+      tc::RowsYBwd prm{logits_y, y_f32, dy, K, 1.f / c.temperature, inv_bg, reinterpret_cast<bf16*>(dlogits_y), Kp,
+                       ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr};
+      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Y_BWD, prm, B, {dy, logits_y, y_f32}, {{dlogits_y, (size_t)B * Kp * 2}}, st));
+    } else {
     GM_TRY(chain_flush(h, st));
     if (std::is_same<A, bf16>::value && K <= 16 && Kp <= 16) {
       GM_CHECK_CUDA(launch_k(head_y_bwd_row_kernel, dim3(std::max(1, std::min(tc::num_sms(), (B + 127) / 128))), dim3(128), 0, st, true,
@@ -1001,6 +1116,8 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
                              ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr));
     }
     GM_LAUNCHED(h, st, PC_HEADS);
+    }
+    if (spread) GM_TRY(wg_y());                       // filler between the y head and encoder_y's data gradients
     GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st, ey_bias_fused)));
   }
   return 0;

@@ -24,7 +24,17 @@
 namespace gmvae {
 namespace tc {
 
-enum EpiKind : int { EK_NONE = -1, EK_STORE_BF16 = 0, EK_STORE_F32 = 1, EK_BCE = 2, EK_RELUMASK = 3, EK_ATOMIC = 4 };
+enum EpiKind : int { EK_NONE = -1, EK_STORE_BF16 = 0, EK_STORE_F32 = 1, EK_BCE = 2, EK_RELUMASK = 3, EK_ATOMIC = 4,
+                     // "row" jobs: no GEMM, the epilogue warps run a distribution head on a block of 128 rows
+                     EK_ROWS_FIRST = 16, EK_ROWS_Y_FWD = 16, EK_ROWS_Z_FWD = 17, EK_ROWS_Z_BWD = 18, EK_ROWS_Y_BWD = 19 };
+
+// Parameters of the row jobs (same math as head_*_kernel in kernels.cuh; bf16 training step only).
+struct RowsYFwd { const float* logits; const float* u; int K; float inv_T, inv_bg; float* y_f32; bf16* y_act; int ld_yact; float* acc; };
+struct RowsZFwd { const float* enc_out; const float* eps; const float* prior_out; int prior_mode, Z; float c, sigma_min, inv_bg;
+                  bf16* z_act; int ld_z; float* acc; };
+struct RowsZBwd { const float* enc_out; const float* eps; const float* prior_out; const float* dz_dec; int prior_mode, Z; float c, sigma_min, inv_bg;
+                  bf16* d_enc_out; bf16* d_prior_out; int ld_out; float* db_enc; float* db_prior; };
+struct RowsYBwd { const float* logits; const float* y_f32; const float* dy; int K; float inv_T, inv_bg; bf16* dlogits; int ld_out; float* db; };
 template <class Epi> struct epi_kind { static constexpr int value = EK_NONE; };
 template <> struct epi_kind<EpiStore<bf16, EPI_PLAIN>> { static constexpr int value = EK_STORE_BF16; };
 template <> struct epi_kind<EpiStore<float, EPI_PLAIN>> { static constexpr int value = EK_STORE_F32; };
@@ -32,8 +42,9 @@ template <> struct epi_kind<EpiBCE<bf16>> { static constexpr int value = EK_BCE;
 template <> struct epi_kind<EpiReluMask<bf16, bf16>> { static constexpr int value = EK_RELUMASK; };
 template <> struct epi_kind<EpiAtomicAdd> { static constexpr int value = EK_ATOMIC; };
 
-constexpr int CHAIN_MAX_JOBS = 10;
-constexpr int CHAIN_MAX_DEPS = 3;
+constexpr int CHAIN_MAX_JOBS = 40;     // a whole forward + backward pass of the 3-MLP model is 33 jobs
+constexpr int CHAIN_MAX_MAPS = 112;    // tensor maps of all jobs (operands, TMA-stored outputs, ReLU-mask sources)
+constexpr int CHAIN_MAX_DEPS = 4;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 constexpr int CHAIN_EPI_BYTES = 128;
@@ -44,12 +55,12 @@ static_assert(CHAIN_CARVE_BYTES + 512 <= CHAIN_SMEM_BYTES, "shared-memory budget
 
 // counters[base + row_block] >= target.  by_k = 0: the row block of the consumer's own tile;
 // by_k = 1 (weight gradients: the contraction runs over the batch): every row block its k-range covers.
-struct ChainDep { int base, target, by_k, nblocks; };
+struct ChainDep { int base, target, by_k, nblocks, seg2; };   // seg2: only the second K segment reads it (checked when that segment starts)
 
-struct alignas(64) ChainJob {
-  CUtensorMap a1, b1, a2, b2;
-  CUtensorMap c;                     // epilogue operand read by TMA (ReLU-mask source), box = one patch
-  CUtensorMap d;                     // output written by TMA store / reduce-add, box = one patch
+struct alignas(16) ChainJob {
+  int a1, b1, a2, b2;                // indices into ChainParams::maps
+  int c;                             // epilogue operand read by TMA (ReLU-mask source), box = one patch
+  int d;                             // output written by TMA store / reduce-add, box = one patch
   int gw;                            // 16-column chunks per 64-byte patch row: 2 (bf16), 1 (fp32), 0: per-row stores
   int M, N, kb1, kb2, kb_per_split, num_splits;
   int block_n, a_mn, b_mn, kind;
@@ -60,13 +71,16 @@ struct alignas(64) ChainJob {
   ChainDep deps[CHAIN_MAX_DEPS];
   alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
 };
+// Passed by value as the kernel's __grid_constant__ parameter (about 26 KB of the 32 KB parameter space).
 struct ChainParams {
-  int njobs;
+  int njobs, nmaps;
   int* counters;
   long long* trace;    // test hook: clock64 stamps of CTA `trace_cta`, 16 per processed tile (null in production)
   int trace_cta;
+  alignas(64) CUtensorMap maps[CHAIN_MAX_MAPS];
   ChainJob jobs[CHAIN_MAX_JOBS];
 };
+static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space");
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -153,8 +167,8 @@ __device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
 // clipped by the tensor map, and no st.global is issued by the epilogue warps at all.  The ReLU mask
 // source of the backward pass arrives the same way (TMA load of the box into the patch).
 template <class Epi, int KIND>
-__device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* counters, const ChainShared& S, int& it, uint32_t& op_phase,
-                                                   int warp, int lane, long long* trace, int jidx) {
+__device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUtensorMap* maps, int* counters, const ChainShared& S, int& it,
+                                                   uint32_t& op_phase, int warp, int lane, long long* trace, int jidx) {
   constexpr int CW = 16;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
   const int G = gridDim.x;
@@ -262,7 +276,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
             if (mvalid) hbits = __ldcg(epi.relu_bits + (int64_t)((n0 + gcol) >> 5) * epi.ld_bits + m);   // L2: written by another SM in this launch
           } else if (lane == 0) {
             mbar_expect_tx(op_bar, (uint32_t)CHAIN_PATCH_BYTES);
-            tma_load_2d(&J.c, op_bar, S.patches + e * CHAIN_PATCH_BYTES, n0 + gcol, mrow0);
+            tma_load_2d(&maps[J.c], op_bar, S.patches + e * CHAIN_PATCH_BYTES, n0 + gcol, mrow0);
           }
         }
         uint32_t obits = 0; int obits_chunks = 0;
@@ -381,8 +395,8 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
         fence_proxy_async();                                  // generic-proxy writes to the patch -> visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-          if constexpr (KIND == EK_ATOMIC) tma_reduce_add_2d(&J.d, patch, n0 + gcol, mrow0);
-          else tma_store_2d(&J.d, patch, n0 + gcol, mrow0);
+          if constexpr (KIND == EK_ATOMIC) tma_reduce_add_2d(&maps[J.d], patch, n0 + gcol, mrow0);
+          else tma_store_2d(&maps[J.d], patch, n0 + gcol, mrow0);
           bulk_commit();
         }
         if constexpr (KIND == EK_RELUMASK || KIND == EK_BCE) {
@@ -415,6 +429,223 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, int* count
   }
 }
 
+// ---- row jobs ---------------------------------------------------------------------------------
+// Data written earlier in this launch by other SMs is read with ld.global.cg (L2), never through L1.
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+template <int KIND, class P>
+__device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters, const ChainShared& S, int warp, int lane) {
+  const P prm = *reinterpret_cast<const P*>(J.epi);
+  const int G = gridDim.x;
+  const int first = (((int)blockIdx.x - J.tile_base) % G + G) % G;
+  if (first >= J.total_tiles) return;
+  const int M = J.M;
+  const int et = (int)threadIdx.x - 64;                 // 0 .. 511
+  constexpr int NT = EPI_WARPS * 32;
+  float red_acc = 0.f;                                   // kl / nent partial of this thread over the job's tiles
+  float cs[16];                                          // column-sum partials (bias gradients) of this thread
+#pragma unroll
+  for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+  for (int l = first; l < J.total_tiles; l += G) {
+    const int mb = l, m0 = mb * BLOCK_M;
+    const int rows = min(BLOCK_M, M - m0);
+    if (lane == 0) {
+      for (int d = 0; d < J.ndeps; ++d) wait_counter(counters + J.deps[d].base + mb, J.deps[d].target);
+    }
+    __syncwarp();
+    if constexpr (KIND == EK_ROWS_Z_FWD) {
+      const int Z = prm.Z, tpr = Z >> 2;
+      for (int t = et; t < rows * tpr; t += NT) {
+        const int b = m0 + t / tpr, j = (t % tpr) * 4;
+        const float4 mu = ldcg4(prm.enc_out + (int64_t)b * 2 * Z + j), raw = ldcg4(prm.enc_out + (int64_t)b * 2 * Z + Z + j);
+        const float4 e4 = ldcg4(prm.eps + (int64_t)b * Z + j);
+        float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp;
+        if (prm.prior_mode == 2) { mp = ldcg4(prm.prior_out + (int64_t)b * 2 * Z + j); rp = ldcg4(prm.prior_out + (int64_t)b * 2 * Z + Z + j); }
+        const float* MU = &mu.x; const float* RAW = &raw.x; const float* E = &e4.x; const float* MP = &mp.x; const float* RP = &rp.x;
+        float z[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float sg = fmaxf(softplus_f(RAW[q] + prm.c), prm.sigma_min);
+          z[q] = fmaf(sg, E[q], MU[q]);
+          const float logq = -0.5f * E[q] * E[q] - logf(sg);
+          float logp = 0.f;
+          if (prm.prior_mode == 0) {
+            logp = -0.5f * z[q] * z[q];
+          } else if (prm.prior_mode == 2) {
+            const float sp = fmaxf(softplus_f(RP[q] + prm.c), prm.sigma_min);
+            const float tt = (z[q] - MP[q]) / sp;
+            logp = -0.5f * tt * tt - logf(sp);
+          }
+          red_acc += logq - logp;
+        }
+        *reinterpret_cast<uint2*>(prm.z_act + (int64_t)b * prm.ld_z + j) = make_uint2(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]));
+      }
+    } else if constexpr (KIND == EK_ROWS_Z_BWD) {
+      const int Z = prm.Z, tpr = Z >> 2;                 // NT % tpr == 0 (checked by the host): a thread keeps its 4 columns
+      const int j = (et % tpr) * 4;
+      for (int t = et; t < rows * tpr; t += NT) {
+        const int b = m0 + t / tpr;
+        const float4 mu = ldcg4(prm.enc_out + (int64_t)b * 2 * Z + j), raw = ldcg4(prm.enc_out + (int64_t)b * 2 * Z + Z + j);
+        const float4 e4 = ldcg4(prm.eps + (int64_t)b * Z + j), dzd = ldcg4(prm.dz_dec + (int64_t)b * Z + j);
+        float4 mp = make_float4(0.f, 0.f, 0.f, 0.f), rp = mp;
+        if (prm.prior_mode == 2) { mp = ldcg4(prm.prior_out + (int64_t)b * 2 * Z + j); rp = ldcg4(prm.prior_out + (int64_t)b * 2 * Z + Z + j); }
+        const float* MU = &mu.x; const float* RAW = &raw.x; const float* E = &e4.x; const float* DZ = &dzd.x;
+        const float* MP = &mp.x; const float* RP = &rp.x;
+        float g0[4], g1[4], a0[4], a1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float spq = softplus_f(RAW[q] + prm.c);
+          const float sg = fmaxf(spq, prm.sigma_min);
+          const float z = fmaf(sg, E[q], MU[q]);
+          float dz = DZ[q];
+          a0[q] = 0.f; a1[q] = 0.f;
+          if (prm.prior_mode == 0) {
+            dz += z * prm.inv_bg;
+          } else {
+            const float spp = softplus_f(RP[q] + prm.c);
+            const float sp = fmaxf(spp, prm.sigma_min);
+            const float d = z - MP[q];
+            const float isp2 = 1.f / (sp * sp);
+            dz += d * isp2 * prm.inv_bg;
+            const float dsp = (1.f / sp - d * d * isp2 / sp) * prm.inv_bg;
+            a0[q] = __bfloat162float(__float2bfloat16_rn(-d * isp2 * prm.inv_bg));
+            a1[q] = __bfloat162float(__float2bfloat16_rn(spp >= prm.sigma_min ? dsp * sigmoid_f(RP[q] + prm.c) : 0.f));
+          }
+          const float dsg = dz * E[q] - prm.inv_bg / sg;
+          g0[q] = __bfloat162float(__float2bfloat16_rn(dz));
+          g1[q] = __bfloat162float(__float2bfloat16_rn(spq >= prm.sigma_min ? dsg * sigmoid_f(RAW[q] + prm.c) : 0.f));
+          cs[q] += g0[q]; cs[4 + q] += g1[q]; cs[8 + q] += a0[q]; cs[12 + q] += a1[q];     // sums of the values as stored
+        }
+        *reinterpret_cast<uint2*>(prm.d_enc_out + (int64_t)b * prm.ld_out + j) = make_uint2(pack_bf16x2(g0[0], g0[1]), pack_bf16x2(g0[2], g0[3]));
+        *reinterpret_cast<uint2*>(prm.d_enc_out + (int64_t)b * prm.ld_out + Z + j) = make_uint2(pack_bf16x2(g1[0], g1[1]), pack_bf16x2(g1[2], g1[3]));
+        if (prm.prior_mode == 2) {
+          *reinterpret_cast<uint2*>(prm.d_prior_out + (int64_t)b * prm.ld_out + j) = make_uint2(pack_bf16x2(a0[0], a0[1]), pack_bf16x2(a0[2], a0[3]));
+          *reinterpret_cast<uint2*>(prm.d_prior_out + (int64_t)b * prm.ld_out + Z + j) = make_uint2(pack_bf16x2(a1[0], a1[1]), pack_bf16x2(a1[2], a1[3]));
+        }
+      }
+    } else if constexpr (KIND == EK_ROWS_Y_FWD) {
+      const int K = prm.K;
+      if (et < rows) {
+        const int row = m0 + et;
+        float lg[16], a[16];
+        float ml = -INFINITY, ma = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          lg[k] = -INFINITY; a[k] = -INFINITY;
+          if (k < K) {
+            lg[k] = __ldcg(prm.logits + (int64_t)row * K + k);
+            a[k] = (lg[k] - logf(-logf(__ldcg(prm.u + (int64_t)row * K + k)))) * prm.inv_T;
+          }
+          ml = fmaxf(ml, lg[k]); ma = fmaxf(ma, a[k]);
+        }
+        float sl = 0.f, sa = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < K) { a[k] = expf(a[k] - ma); sl += expf(lg[k] - ml); sa += a[k]; }
+        const float lse = ml + logf(sl), inv_sa = 1.f / sa;
+        float y[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          y[k] = 0.f;
+          if (k < K) {
+            const float logp = lg[k] - lse;
+            red_acc += expf(logp) * logp;
+            y[k] = a[k] * inv_sa;
+            prm.y_f32[(int64_t)row * K + k] = y[k];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(prm.y_act + (int64_t)row * prm.ld_yact);
+        dst[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        if (prm.ld_yact > 8) dst[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+      }
+    } else if constexpr (KIND == EK_ROWS_Y_BWD) {
+      const int K = prm.K;
+      if (et < rows) {
+        const int row = m0 + et;
+        float lg[16], y[16], g[16];
+        float ml = -INFINITY, ydy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          lg[k] = -INFINITY; y[k] = 0.f; g[k] = 0.f;
+          if (k < K) {
+            lg[k] = __ldcg(prm.logits + (int64_t)row * K + k);
+            y[k] = __ldcg(prm.y_f32 + (int64_t)row * K + k);
+            g[k] = __ldcg(prm.dy + (int64_t)row * K + k);
+          }
+          ml = fmaxf(ml, lg[k]);
+          ydy += y[k] * g[k];
+        }
+        float sl = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < K) sl += expf(lg[k] - ml);
+        const float lse = ml + logf(sl);
+        float plogp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < K) { lg[k] -= lse; plogp += expf(lg[k]) * lg[k]; }
+        float o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          o[k] = 0.f;
+          if (k < K) {
+            o[k] = __bfloat162float(__float2bfloat16_rn(y[k] * (g[k] - ydy) * prm.inv_T + expf(lg[k]) * (lg[k] - plogp) * prm.inv_bg));
+            cs[k] += o[k];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(prm.dlogits + (int64_t)row * prm.ld_out);
+        dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        if (prm.ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+      }
+    }
+    // release the row block: the rows are read by later jobs through TMA (async proxy) and by plain loads
+    fence_proxy_async_global();
+    __syncwarp();
+    if (lane == 0 && J.sig_base >= 0) {
+      __threadfence();
+      atomicAdd(counters + J.sig_base + mb, 1);
+    }
+  }
+  // ---- per-job reductions of this CTA
+  if constexpr (KIND == EK_ROWS_Z_FWD || KIND == EK_ROWS_Y_FWD) {
+    const float s = warp_sum(red_acc);
+    if (lane == 0 && s != 0.f) acc_add(prm.acc, KIND == EK_ROWS_Z_FWD ? ACC_KL : ACC_NENT, s * prm.inv_bg);
+  }
+  if constexpr (KIND == EK_ROWS_Z_BWD || KIND == EK_ROWS_Y_BWD) {
+    // bias gradients: register partials -> CTA accumulator in shared memory -> one atomic per column
+    float* const scs = S.scs_all;                        // 256 floats
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    for (int i = et; i < 256; i += NT) scs[i] = 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if constexpr (KIND == EK_ROWS_Z_BWD) {
+      const int Z = prm.Z, j = (et % (Z >> 2)) * 4;
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (cs[4 * p4 + q] != 0.f) atomicAdd(scs + p4 * Z + j + q, cs[4 * p4 + q]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float t = warp_sum(cs[k]);
+        if (lane == 0 && t != 0.f) atomicAdd(scs + k, t);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if constexpr (KIND == EK_ROWS_Z_BWD) {
+      const int Z = prm.Z;
+      for (int col = et; col < 4 * Z; col += NT) {
+        const int p4 = col / Z, jj = col % Z;
+        const float t = scs[col];
+        if (t != 0.f && (p4 < 2 || prm.prior_mode == 2)) atomicAdd((p4 < 2 ? prm.db_enc : prm.db_prior) + (p4 & 1) * Z + jj, t);
+      }
+    } else {
+      if (et < prm.K && scs[et] != 0.f && prm.db) atomicAdd(prm.db + et, scs[et]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int STAGES = CHAIN_STAGES, STAGE_BYTES = CHAIN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -436,13 +667,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   long long* const trace = (p.trace && c == p.trace_cta) ? p.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
-    for (int j = 0; j < p.njobs; ++j) {
-      tma_prefetch_desc(&p.jobs[j].a1);
-      tma_prefetch_desc(&p.jobs[j].b1);
-      if (p.jobs[j].kb2 > 0) { tma_prefetch_desc(&p.jobs[j].a2); tma_prefetch_desc(&p.jobs[j].b2); }
-      if (p.jobs[j].gw > 0) tma_prefetch_desc(&p.jobs[j].d);
-      if (p.jobs[j].kind == EK_RELUMASK) tma_prefetch_desc(&p.jobs[j].c);
-    }
+    for (int i = 0; i < p.nmaps; ++i) tma_prefetch_desc(&p.maps[i]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&op_bar[s], 1);
@@ -464,6 +689,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
       int pit = 0;
       for (int j = 0; j < p.njobs; ++j) {
         const ChainJob& J = p.jobs[j];
+        if (J.kind >= EK_ROWS_FIRST) continue;              // row jobs have no GEMM
         const int tiles_n = J.tiles_n, tiles_mn = J.tiles_mn, BN = J.block_n, kb1 = J.kb1, kb_total = J.kb1 + J.kb2;
         const uint32_t tx_bytes = (uint32_t)(A_STAGE_BYTES + BN * BLOCK_K * 2);
         const int first = ((c - J.tile_base) % G + G) % G;
@@ -477,6 +703,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
           if (J.ndeps > 0) {
             for (int d = 0; d < J.ndeps; ++d) {
               const ChainDep& D = J.deps[d];
+              if (D.seg2) continue;
               if (!D.by_k) {
                 wait_counter(p.counters + D.base + mb, D.target);
               } else {
@@ -488,10 +715,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
           }
           if (tr) trace[16 * pit + 1] = clock64();
           for (int kb = kb_begin; kb < kb_end; ++kb) {
+            if (kb == kb1 && J.ndeps > 0) {
+              // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
+              bool any = false;
+              for (int d = 0; d < J.ndeps; ++d)
+                if (J.deps[d].seg2) { wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
+              if (any) fence_proxy_async_global();
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             const bool seg2 = kb >= kb1;
-            const CUtensorMap* ta = seg2 ? &J.a2 : &J.a1;
-            const CUtensorMap* tb = seg2 ? &J.b2 : &J.b1;
+            const CUtensorMap* ta = &p.maps[seg2 ? J.a2 : J.a1];
+            const CUtensorMap* tb = &p.maps[seg2 ? J.b2 : J.b1];
             const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
@@ -520,6 +754,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
       int it = 0;
       for (int j = 0; j < p.njobs; ++j) {
         const ChainJob& J = p.jobs[j];
+        if (J.kind >= EK_ROWS_FIRST) continue;
         const int tiles_mn = J.tiles_mn, kb_total = J.kb1 + J.kb2;
         const int a_mn = J.a_mn, b_mn = J.b_mn;
         const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -567,11 +802,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane); break;
+        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane); break;
+        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd>(J, p.counters, S, warp, lane); break;
+        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd>(J, p.counters, S, warp, lane); break;
         default: break;
       }
     }
