@@ -346,7 +346,7 @@ def run_gpu_arm(args, w):
                 "ms_per_step": e2e_ms / args.steps, "note": "pinned uint8 batch -> H2D (copy stream, double-buffered) -> graph -> D2H loss"},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": traffic, "kernel": f"gemm_tc_kernel (tcgen05; {tc_launches} launches/step, {tc_ms:.3f} ms/step by CUDA events)",
+                     "traffic": traffic, "kernel": f"gemm_chain_kernel (tcgen05 GEMM jobs + fused epilogues/heads; {tc_launches} launches/step, {tc_ms:.3f} ms/step by CUDA events)",
                      "peak_source": peak_src, "flop_per_sample": fps, "tc_flop_per_sample": tc_flops_per_sample(w, args.objective),
                      "whole_step_tflops": step_tf, "whole_step_frac": step_tf / peak_tf},
         "kernel_profile": prof,

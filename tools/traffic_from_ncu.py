@@ -15,7 +15,7 @@ def to_bytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 tot = 0.0; n = 0; t_us = 0.0
 for d in rows[2:]:
-    if len(d) != len(hdr) or "gemm_tc_kernel" not in d[col("Kernel Name")]:
+    if len(d) != len(hdr) or not any(k in d[col("Kernel Name")] for k in ("gemm_tc_kernel", "gemm_chain_kernel")):
         continue
     tot += to_bytes(d[col("dram__bytes_read.sum")], units[col("dram__bytes_read.sum")])
     tot += to_bytes(d[col("dram__bytes_write.sum")], units[col("dram__bytes_write.sum")])
