@@ -10,8 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgmvae_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "epilogue.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "kernels.cuh",
-           os.path.join("..", "..", "include", "gmvae_abi.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "gmvae_abi.h")]
 
 
 def nccl_dirs():
