@@ -122,6 +122,9 @@ struct LinView {
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
        DBG_NO_PDL = 128, DBG_NO_CHAIN = 512, DBG_NO_ROW_JOBS = 1024, DBG_NO_SPREAD = 4096,
+       DBG_ROW_JOBS = 8192 /* force the distribution heads to run as row jobs of the chained kernel (the whole forward + backward
+                              pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
+                              vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
        DBG_RELU_BITS = 2048 /* 1-bit ReLU masks between the chained forward and backward jobs: measured 1 % slower than
                                reading the bf16 activation through TMA, kept as an experiment */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
@@ -173,6 +176,7 @@ struct gmvae_handle {
   int* chain_counters = nullptr; int chain_counter_cap = 0, chain_counter_next = 0;
   long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
   bool chain_flush_after = false;
+  bool row_jobs = false;                          // this step: distribution heads run as row jobs of the chained kernel
   bool last_gemm_chained = false;                 // set by the GEMM dispatch: the last GEMM became a job of the chain
   std::map<const void*, bool> relu_bits_valid;    // hidden activation -> its 1-bit ReLU mask was written this step
   // graph
@@ -390,7 +394,8 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   if (h->chain.njobs == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
     attr_set = true;
   }
   h->chain.counters = h->chain_counters;
@@ -398,7 +403,16 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain.trace_cta = h->chain_trace_cta;
   h->chain_launch_idx++;
   const int grid = std::min(h->chain_tiles, tc::num_sms());
-  GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+  if (h->chain.njobs <= tc::CHAIN_SMALL_JOBS && h->chain.nmaps <= tc::CHAIN_SMALL_MAPS) {
+    static tc::ChainParamsSmall small;                      // the launch copies it
+    small.njobs = h->chain.njobs; small.nmaps = h->chain.nmaps; small.counters = h->chain.counters;
+    small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta;
+    memcpy(small.maps, h->chain.maps, sizeof(CUtensorMap) * h->chain.nmaps);
+    memcpy(small.jobs, h->chain.jobs, sizeof(tc::ChainJob) * h->chain.njobs);
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
+  } else {
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParams>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+  }
   h->chain.njobs = 0; h->chain.nmaps = 0; h->chain_tiles = 0; h->chain_writers.clear();
   h->launches++;
   if (h->profiling) GM_TRY(profile_mark(h, st, 0 /*PC_TC_GEMM*/));
@@ -723,7 +737,7 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
     int64_t ld = i == 0 ? ld0 : ldp(m.layers[i - 1].out);
     LinView L = view(h, m.layers[i], 0, i == 0 ? in0_cols : -1);
     EpiStore<A> epi{b.hid[i], (int64_t)ldp(m.layers[i].out), L.b, nullptr, 0, 1, 1.f};
-    if (h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = b.bits[i]; epi.ld_bits = round_up(M, 32); }
+    if (tc::CHAIN_RELU_BITS && h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = b.bits[i]; epi.ld_bits = round_up(M, 32); }
     GM_TRY(lin_fwd<A>(h, in, ld, M, L, epi, st));
     h->relu_bits_valid[b.hid[i]] = epi.relu_bits != nullptr && h->last_gemm_chained;
   }
@@ -848,7 +862,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
     }
-    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS);
+    const bool rows_ok = h->chain_on && h->row_jobs;
     if (rows_ok && K <= 16 && Kp <= 16 && u) {
       // q(y|x) head as a job of the chain: no launch, no pipeline drain between encoder_y and encoder_gmm
       tc::RowsYFwd prm{logits_y, u, K, 1.f / c.temperature, inv_bg, y_f32, reinterpret_cast<bf16*>(y_act), Kp, acc};
@@ -875,7 +889,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
       } else {
         EpiStore<A> epi{enc.hid[0], hid_ld(0), Lx.b, nullptr, 0, 1, 1.f};
-        if (h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = enc.bits[0]; epi.ld_bits = round_up(B, 32); }
+        if (tc::CHAIN_RELU_BITS && h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = enc.bits[0]; epi.ld_bits = round_up(B, 32); }
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
         h->relu_bits_valid[enc.hid[0]] = epi.relu_bits != nullptr && h->last_gemm_chained;
       }
@@ -921,6 +935,9 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   h->relu_bits_valid.clear();
   h->chain_counters = h->buf<int>("chain.counters");
   h->chain_on = std::is_same<A, bf16>::value && h->bf16_mode() && h->chain_counters && !(h->debug_flags & (DBG_NO_TC | DBG_NO_CHAIN));
+  // Heads as row jobs (one launch for the whole pass) pay off once there are enough 128-row blocks to keep the SMs busy
+  // across the dependent thin jobs; below that the heads run as separate kernels between chained launches.
+  h->row_jobs = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && (B >= 32 * tc::BLOCK_M || (h->debug_flags & DBG_ROW_JOBS));
   if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
   int r = forward_backward_body<A>(h, x_u8, B, Bg, eps_in, u_in, st);
   if (r == 0) r = chain_flush(h, st);
@@ -967,7 +984,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     int64_t n = (int64_t)B * Z;
     const bool v4 = std::is_same<A, bf16>::value && Z % 4 == 0 && Z <= 256 && aligned16(eps) && aligned16(enc_out) &&
                     (prior_mode != 2 || aligned16(prior_out));
-    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && v4 && prior_mode != 1 && z_f32 == nullptr;
+    const bool rows_ok = h->chain_on && h->row_jobs && v4 && prior_mode != 1 && z_f32 == nullptr;
     if (rows_ok) {
       tc::RowsZFwd prm{enc_out, eps, prior_out, prior_mode, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, reinterpret_cast<bf16*>(z_act), Zp, acc};
       GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_FWD, prm, B, {enc_out, eps, prior_out}, {{z_act, (size_t)B * Zp * 2}}, st));
@@ -1012,7 +1029,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   // Order of the jobs: the data gradients form the critical path (each depends on the one before); the weight
   // gradients only read finished tensors, so in the chained kernel they are placed where that path has bubbles:
   // right after the thin jobs (dz, dy, the heads), whose dependants would otherwise wait out a full tile latency.
-  const bool spread = h->chain_on && !(h->debug_flags & DBG_NO_SPREAD) && !(h->comm && h->world > 1 && h->overlap_comm);
+  const bool spread = h->chain_on && h->row_jobs && !(h->debug_flags & DBG_NO_SPREAD) && !(h->comm && h->world > 1 && h->overlap_comm);
   std::vector<std::function<int()>> wg_dec;          // weight gradients of the two lowest decoder layers
   GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, B, st, dec_bias_fused, 0, spread ? &wg_dec : nullptr,
                              std::min(2, nl - 1))));
@@ -1030,7 +1047,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   {
     int64_t n = (int64_t)B * Z;
     enc_bias_fused = Z <= 256 && !(h->debug_flags & DBG_NO_FUSED_COLSUM);
-    const bool rows_ok = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && enc_bias_fused && prior_mode != 1 &&
+    const bool rows_ok = h->chain_on && h->row_jobs && enc_bias_fused && prior_mode != 1 &&
                          (Z == 4 || Z == 8 || Z == 16 || Z == 32 || Z == 64) && aligned16(eps) && aligned16(enc_out) && aligned16(dz) &&
                          (prior_mode != 2 || aligned16(prior_out));
     if (rows_ok) {
@@ -1100,7 +1117,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     if (!spread) GM_TRY(wg_y());
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
-    if (h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && K <= 16 && Kp <= 16) {
+    if (h->chain_on && h->row_jobs && K <= 16 && Kp <= 16) {
       tc::RowsYBwd prm{logits_y, y_f32, dy, K, 1.f / c.temperature, inv_bg, reinterpret_cast<bf16*>(dlogits_y), Kp,
                        ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr};
       GM_TRY(chain_add_rows(h, tc::EK_ROWS_Y_BWD, prm, B, {dy, logits_y, y_f32}, {{dlogits_y, (size_t)B * Kp * 2}}, st));

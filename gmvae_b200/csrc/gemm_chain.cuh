@@ -42,6 +42,11 @@ template <> struct epi_kind<EpiBCE<bf16>> { static constexpr int value = EK_BCE;
 template <> struct epi_kind<EpiReluMask<bf16, bf16>> { static constexpr int value = EK_RELUMASK; };
 template <> struct epi_kind<EpiAtomicAdd> { static constexpr int value = EK_ATOMIC; };
 
+#ifdef GMVAE_RELU_BITS
+constexpr bool CHAIN_RELU_BITS = true;    // experiment: 1-bit ReLU masks between forward and backward jobs (1 % slower, see engine.cu)
+#else
+constexpr bool CHAIN_RELU_BITS = false;
+#endif
 constexpr int CHAIN_MAX_JOBS = 40;     // a whole forward + backward pass of the 3-MLP model is 33 jobs
 constexpr int CHAIN_MAX_MAPS = 112;    // tensor maps of all jobs (operands, TMA-stored outputs, ReLU-mask sources)
 constexpr int CHAIN_MAX_DEPS = 4;
@@ -71,15 +76,21 @@ struct alignas(16) ChainJob {
   ChainDep deps[CHAIN_MAX_DEPS];
   alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
 };
-// Passed by value as the kernel's __grid_constant__ parameter (about 26 KB of the 32 KB parameter space).
-struct ChainParams {
+// Passed by value as the kernel's __grid_constant__ parameter.  Two capacities: the recording buffer (a whole
+// forward + backward pass in one launch, about 26 KB of the 32 KB parameter space) and a small one (8 KB) used when
+// the recorded section fits -- the parameter block is copied at every launch, ~3 us for the large one.
+template <int MAXJ, int MAXM>
+struct ChainParamsT {
   int njobs, nmaps;
   int* counters;
   long long* trace;    // test hook: clock64 stamps of CTA `trace_cta`, 16 per processed tile (null in production)
   int trace_cta;
-  alignas(64) CUtensorMap maps[CHAIN_MAX_MAPS];
-  ChainJob jobs[CHAIN_MAX_JOBS];
+  alignas(64) CUtensorMap maps[MAXM];
+  ChainJob jobs[MAXJ];
 };
+constexpr int CHAIN_SMALL_JOBS = 10, CHAIN_SMALL_MAPS = 44;
+typedef ChainParamsT<CHAIN_MAX_JOBS, CHAIN_MAX_MAPS> ChainParams;
+typedef ChainParamsT<CHAIN_SMALL_JOBS, CHAIN_SMALL_MAPS> ChainParamsSmall;
 static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space");
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -266,7 +277,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
         uint32_t hbits = 0;
         bool use_bits = false;
         if constexpr (KIND == EK_RELUMASK) {
-          use_bits = epi.relu_bits != nullptr;
+          use_bits = CHAIN_RELU_BITS && epi.relu_bits != nullptr;
           if (!use_bits) fence_proxy_async();   // this warp's earlier generic reads of the patch precede the TMA write
         }
         __syncwarp();
@@ -339,7 +350,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
                   if (epi.relu == 1) v[i] = fmaxf(v[i], 0.f);
                   else if (epi.relu == 2) v[i] = sigmoid_f(v[i] + epi.shift);
                 }
-                if (epi.relu_bits) {
+                if (CHAIN_RELU_BITS && epi.relu_bits) {
                   // [v == 0] for v >= +0 is the top bit of bits(v) - 1; one funnel shift per element appends it
                   // (element e of the group ends at bit 31 - e; complemented when the word is stored)
 #pragma unroll
@@ -387,7 +398,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
           }
         }
         if constexpr (KIND == EK_STORE_BF16) {
-          if (epi.relu_bits && mvalid) {
+          if (CHAIN_RELU_BITS && epi.relu_bits && mvalid) {
             if (obits_chunks < 2) obits = (obits << 16) | 0xFFFFu;     // the group's second chunk lies beyond N
             epi.relu_bits[(int64_t)((n0 + gcol) >> 5) * epi.ld_bits + m] = ~obits;   // a warp's 32 rows: one 128-byte line
           }
@@ -646,7 +657,8 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __grid_constant__ ChainParams p) {
+template <class Params>
+__global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __grid_constant__ Params p) {
   constexpr int STAGES = CHAIN_STAGES, STAGE_BYTES = CHAIN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -807,10 +819,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
         case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
         case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+#ifndef GMVAE_NO_ROWS
         case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane); break;
         case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane); break;
         case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd>(J, p.counters, S, warp, lane); break;
         case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd>(J, p.counters, S, warp, lane); break;
+#endif
         default: break;
       }
     }

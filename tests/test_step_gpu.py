@@ -48,6 +48,24 @@ def test_parity_bf16(name):
         assert v < 3 * TOL["bf16"], (name, "vs bf16 rounding model", k, v)
 
 
+# Variants of the launch plan of the bf16 step (GMVAE_DEBUG_FLAGS, engine.cu): the default at these batch sizes is five
+# chained-GEMM launches with the heads as kernels in between; 8192 = heads as row jobs, the whole pass in ONE launch
+# (the default from 4096 samples up); 512 = no chaining, one launch per GEMM; 8192|4096 = one launch, weight gradients
+# not spread into the dependency bubbles.
+@pytest.mark.parametrize("flags", ["8192", "512", "12288"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "tiny_gmvae", "nohidden_gmvae", "run_train_sh"])
+def test_parity_bf16_launch_plans(name, flags, monkeypatch):
+    monkeypatch.setenv("GMVAE_DEBUG_FLAGS", flags)
+    terr, _ = run_parity(CONFIGS[name], "bf16")
+    for k, v in terr.items():
+        assert v < TOL["bf16"], (name, flags, k, v)
+    _, gerr_model = run_parity(CONFIGS[name], "bf16", rounding_model=Bf16Model(True))
+    flat = sum(v * v for v in gerr_model.values()) ** 0.5 / len(gerr_model) ** 0.5
+    assert flat < 1.5 * TOL["bf16"], (name, flags, "rms over tensors vs bf16 rounding model", flat)
+    for k, v in gerr_model.items():
+        assert v < 3 * TOL["bf16"], (name, flags, "vs bf16 rounding model", k, v)
+
+
 MARGINAL_CASES = ["tiny_gmvae", "cfg3", "run_train_sh"]
 
 
