@@ -999,27 +999,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   griddep_wait();
   griddep_launch();
   __shared__ float lr_t_s;
+  __shared__ int e0_s;
   if (loss_out && blockIdx.x == 0 && threadIdx.x == 32) {   // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
     float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
     loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
   }
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x * 4;
   if (threadIdx.x == 0) {
     double t = (double)(st->step + 1);
     lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
     // global_step += 1 once every block of this launch has read it: the last block to get here does it
     __threadfence();
     if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) { st->adam_blocks = 0; st->step += 1; }
+  } else if (threadIdx.x == 64) {
+    // the weight matrix the block's first element belongs to (entries are sorted by flat offset); the block's
+    // 1024 elements almost always lie in the same matrix, so the threads only step forward from here
+    int lo = 0, hi = n_shadows;                             // first entry with off > i0
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (shadows[mid].off <= i0) lo = mid + 1; else hi = mid; }
+    e0_s = lo - 1;
   }
   __syncthreads();
   const float lr_t = lr_t_s;
-  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int64_t i = i0 + (int64_t)threadIdx.x * 4;
   if (i >= n) return;
-  // the weight matrix this group of 4 belongs to (tensors start on 16-byte boundaries, so a group never straddles two)
-  int lo = 0, hi = n_shadows;                               // first entry with off > i
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (shadows[mid].off <= i) lo = mid + 1; else hi = mid; }
+  // tensors start on 16-byte boundaries, so a group of 4 never straddles two
+  int e = e0_s;
+  while (e + 1 < n_shadows && shadows[e + 1].off <= i) ++e;
   bf16* wb = nullptr; int cols = 0, ld_w = 0; int64_t rel = 0, lim = 0;
-  if (lo > 0) {
-    const ShadowEntry& E = shadows[lo - 1];
+  if (e >= 0) {
+    const ShadowEntry& E = shadows[e];
     rel = i - E.off; lim = (int64_t)E.rows * E.cols;
     if (rel < lim) { wb = E.w_bf16; cols = E.cols; ld_w = E.ld_w; }
   }
@@ -1040,8 +1048,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int64_t e = rel + j;
-          if (e < lim) wb[(e / cols) * ld_w + (e % cols)] = __float2bfloat16_rn(P[j]);
+          const int64_t el = rel + j;
+          if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(P[j]);
         }
       }
     }
@@ -1051,7 +1059,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
       m[k] = mk; v[k] = vk;
       p[k] -= lr_t * mk / (sqrtf(vk) + eps);
-      if (wb) { const int64_t e = rel + (k - i); if (e < lim) wb[(e / cols) * ld_w + (e % cols)] = __float2bfloat16_rn(p[k]); }
+      if (wb) { const int64_t el = rel + (k - i); if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(p[k]); }
     }
   }
 }

@@ -37,7 +37,7 @@ def launches(src, dst, cmd):
         t = to_us(*d["gpu__time_duration.sum"])
         tp = d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("", ""))[0]
         items.append((short_name(d["name"]), d["grid"], t, tp))
-    starts = [i for i, it in enumerate(items) if it[0].startswith("convert_x")]
+    starts = [i for i, it in enumerate(items) if it[0].startswith(("convert_x", "prologue_kernel"))]
     step = items[starts[-2]:starts[-1]] if len(starts) >= 2 else items
     tot = sum(i[2] for i in step)
     agg = collections.OrderedDict()
