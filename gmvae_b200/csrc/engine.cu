@@ -121,7 +121,7 @@ struct LinView {
 };
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
-       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512, DBG_NO_ROW_JOBS = 1024, DBG_NO_SPREAD = 4096,
+       DBG_NO_PDL = 128, DBG_NO_CHAIN = 512, DBG_NO_ROW_JOBS = 1024, DBG_NO_SPREAD = 4096, DBG_NO_FUSE_HEADS = 16384,
        DBG_ROW_JOBS = 8192 /* force the distribution heads to run as row jobs of the chained kernel (the whole forward + backward
                               pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
                               vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
@@ -177,6 +177,9 @@ struct gmvae_handle {
   long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
   bool chain_flush_after = false;
   bool row_jobs = false;                          // this step: distribution heads run as row jobs of the chained kernel
+  // a y head to be fused into the epilogue of the next thin fp32 GEMM job (set by the step driver, consumed by chain_add)
+  struct FuseReq { int kind = 0; unsigned char prm[tc::CHAIN_EPI2_BYTES]; std::vector<std::pair<const void*, size_t>> writes; bool consumed = false; };
+  FuseReq fuse_next;
   bool last_gemm_chained = false;                 // set by the GEMM dispatch: the last GEMM became a job of the chain
   std::map<const void*, bool> relu_bits_valid;    // hidden activation -> its 1-bit ReLU mask was written this step
   // graph
@@ -534,6 +537,14 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   }
   memset(J.epi, 0, sizeof(J.epi));
   memcpy(J.epi, &epi, sizeof(Epi));
+  J.fuse = 0;
+  if (h->fuse_next.kind != 0 && tc::epi_kind<Epi>::value == tc::EK_STORE_F32 && N <= 16 && J.sig_base >= 0) {
+    J.fuse = h->fuse_next.kind;
+    memcpy(J.epi2, h->fuse_next.prm, sizeof(J.epi2));
+    for (const auto& w : h->fuse_next.writes)
+      if (w.first) h->chain_writers.push_back({reinterpret_cast<const char*>(w.first), reinterpret_cast<const char*>(w.first) + w.second, h->chain.njobs});
+    h->fuse_next.consumed = true;
+  }
   h->chain_tiles += J.total_tiles;
   h->chain.njobs++;
   h->last_gemm_chained = true;
@@ -857,13 +868,26 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
     float* prior_out = h->buf<float>("prior_out");
     // q(y|x): encoder_y MLP, logits in fp32 (gmvae.py:238)
     GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, Dp, D, B, 0, st));
+    const bool rows_ok = h->chain_on && h->row_jobs;
+    bool y_fused = false;
     {
       const Linear& l = h->encoder_y.layers[nl - 1];
       EpiStore<float> epi{logits_y, (int64_t)K, h->params + l.b_off, nullptr, 0, 0, 1.f};
+      if (rows_ok && K <= 16 && Kp <= 16 && u && !(h->debug_flags & DBG_NO_FUSE_HEADS)) {
+        // the q(y|x) head runs in the epilogue of this GEMM (the lane holds the whole row of K logits)
+        tc::RowsYFwd prm{logits_y, u, K, 1.f / c.temperature, inv_bg, y_f32, reinterpret_cast<bf16*>(y_act), Kp, acc};
+        h->fuse_next = gmvae_handle::FuseReq();
+        h->fuse_next.kind = tc::EK_ROWS_Y_FWD;
+        memcpy(h->fuse_next.prm, &prm, sizeof(prm));
+        h->fuse_next.writes = {{y_f32, (size_t)B * K * 4}, {y_act, (size_t)B * Kp * 2}};
+      }
       GM_TRY(lin_fwd<A>(h, nl == 1 ? x_act : ey.hid[nl - 2], nl == 1 ? Dp : hid_ld(nl - 2), B, view(h, l), epi, st));
+      y_fused = h->fuse_next.consumed;
+      h->fuse_next = gmvae_handle::FuseReq();
     }
-    const bool rows_ok = h->chain_on && h->row_jobs;
-    if (rows_ok && K <= 16 && Kp <= 16 && u) {
+    if (y_fused) {
+      // nothing to do: y, its bf16 operand row and the entropy term were produced by the logits job
+    } else if (rows_ok && K <= 16 && Kp <= 16 && u) {
       // q(y|x) head as a job of the chain: no launch, no pipeline drain between encoder_y and encoder_gmm
       tc::RowsYFwd prm{logits_y, u, K, 1.f / c.temperature, inv_bg, y_f32, reinterpret_cast<bf16*>(y_act), Kp, acc};
       GM_TRY(chain_add_rows(h, tc::EK_ROWS_Y_FWD, prm, B, {logits_y, u},
@@ -1097,10 +1121,23 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     const Linear& lp = h->prior_gmm.layers[0];
     LinView Lp = view(h, lp);
     const bool dy_two_seg = tc_ok_dgrad<A>(h, dh0, ld_dh0, Ly) && tc_ok_dgrad<A>(h, d_prior_out, Z2p, Lp) && !(h->debug_flags & DBG_NO_TWO_SEG);
+    const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
+    bool yb_fused = false;
     {
       EpiStore<float> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
+      if (dy_two_seg && h->chain_on && h->row_jobs && K <= 16 && Kp <= 16 && ey_bias_fused && !(h->debug_flags & DBG_NO_FUSE_HEADS)) {
+        // the backward of the q(y|x) head runs in the epilogue of the dy GEMM; dy itself never reaches memory
+        tc::RowsYBwd prm{logits_y, y_f32, nullptr, K, 1.f / c.temperature, inv_bg, reinterpret_cast<bf16*>(dlogits_y), Kp,
+                         h->grads + h->encoder_y.layers[nl - 1].b_off};
+        h->fuse_next = gmvae_handle::FuseReq();
+        h->fuse_next.kind = tc::EK_ROWS_Y_BWD;
+        memcpy(h->fuse_next.prm, &prm, sizeof(prm));
+        h->fuse_next.writes = {{dlogits_y, (size_t)B * Kp * 2}};
+      }
       if (dy_two_seg) GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st, d_prior_out, Z2p, &Lp)));
       else GM_TRY((lin_dgrad<A>(h, dh0, ld_dh0, B, Ly, e, st)));
+      yb_fused = h->fuse_next.consumed;
+      h->fuse_next = gmvae_handle::FuseReq();
     }
     if (!dy_two_seg) {
       EpiStore<float, EPI_ACCUM> e{dy, (int64_t)K, nullptr, nullptr, 0, 0, 1.f};
@@ -1116,8 +1153,9 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     };
     if (!spread) GM_TRY(wg_y());
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
-    const bool ey_bias_fused = !(h->debug_flags & DBG_NO_FUSED_COLSUM);
-    if (h->chain_on && h->row_jobs && K <= 16 && Kp <= 16) {
+    if (yb_fused) {
+      // dlogits_y and encoder_y's last bias gradient were produced by the dy job
+    } else if (h->chain_on && h->row_jobs && K <= 16 && Kp <= 16) {
       tc::RowsYBwd prm{logits_y, y_f32, dy, K, 1.f / c.temperature, inv_bg, reinterpret_cast<bf16*>(dlogits_y), Kp,
                        ey_bias_fused ? h->grads + h->encoder_y.layers[nl - 1].b_off : (float*)nullptr};
       GM_TRY(chain_add_rows(h, tc::EK_ROWS_Y_BWD, prm, B, {dy, logits_y, y_f32}, {{dlogits_y, (size_t)B * Kp * 2}}, st));

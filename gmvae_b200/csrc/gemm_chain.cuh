@@ -53,6 +53,7 @@ constexpr int CHAIN_MAX_DEPS = 4;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 constexpr int CHAIN_EPI_BYTES = 128;
+constexpr int CHAIN_EPI2_BYTES = 64;
 constexpr int CHAIN_PATCH_BYTES = 2048;   // per epilogue warp: 32 rows x 64 B, the box of one TMA store (SWIZZLE_64B like the tensor map)
 constexpr int CHAIN_CARVE_BYTES = CHAIN_STAGES * CHAIN_STAGE_BYTES + EPI_WARPS * CHAIN_PATCH_BYTES + 256 /*barriers*/ + 256 * 4 /*bias*/ + 256 * 4 /*column sums*/;
 constexpr int CHAIN_SMEM_BYTES = 232448;  // everything an SM offers one CTA (227 KB); the carve-out needs all but 768 bytes of it
@@ -75,6 +76,8 @@ struct alignas(16) ChainJob {
   int epi_dep;                       // index into deps of the job that wrote the epilogue's own operand (ReLU mask source), or -1
   ChainDep deps[CHAIN_MAX_DEPS];
   alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
+  int fuse;                          // EK_STORE_F32 jobs with N <= 16: a y head applied to the row in the epilogue (EK_ROWS_Y_FWD / _BWD), 0 = none
+  alignas(16) unsigned char epi2[CHAIN_EPI2_BYTES];   // its parameters (RowsYFwd / RowsYBwd)
 };
 // Passed by value as the kernel's __grid_constant__ parameter.  Two capacities: the recording buffer (a whole
 // forward + backward pass in one launch, about 26 KB of the 32 KB parameter space) and a small one (8 KB) used when
@@ -166,6 +169,89 @@ __device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
   hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
 }
 
+// ---- q(y|x) head on one row held in registers (K <= 16): shared by the row jobs and the fused epilogues ----
+// Warp-collective (all 32 lanes call; `valid` masks rows beyond the batch) and deliberately NOT inlined: the thin
+// GEMM jobs that host them sit on the critical path of the chain and must not inherit their register footprint.
+// forward: lg = logits (with bias).  Writes y (fp32 + zero-padded bf16 operand row), returns sum_k p log p of the row.
+__device__ __noinline__ float y_head_fwd_row(const float* lg, const RowsYFwd& prm, int64_t row, bool valid) {
+  if (!valid) return 0.f;
+  const int K = prm.K;
+  float a[16];
+  float ml = -INFINITY, ma = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    a[k] = -INFINITY;
+    if (k < K) {
+      a[k] = (lg[k] - logf(-logf(__ldcg(prm.u + row * K + k)))) * prm.inv_T;
+      ml = fmaxf(ml, lg[k]);
+    }
+    ma = fmaxf(ma, a[k]);
+  }
+  float sl = 0.f, sa = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < K) { a[k] = expf(a[k] - ma); sl += expf(lg[k] - ml); sa += a[k]; }
+  const float lse = ml + logf(sl), inv_sa = 1.f / sa;
+  float y[16];
+  float ent = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    y[k] = 0.f;
+    if (k < K) {
+      const float logp = lg[k] - lse;
+      ent += expf(logp) * logp;
+      y[k] = a[k] * inv_sa;
+      prm.y_f32[row * K + k] = y[k];
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(prm.y_act + row * prm.ld_yact);
+  dst[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  if (prm.ld_yact > 8) dst[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+  return ent;
+}
+// backward: g = dy of the row.  Writes dlogits (bf16, zero-padded); the column sums of the stored values over the
+// warp's rows (bias gradient of encoder_y's last layer) are added to the shared-memory accumulator scs[0..K).
+__device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm, int64_t row, bool valid, float* scs) {
+  const int K = prm.K;
+  float lg[16], o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) o[k] = 0.f;
+  if (valid) {
+    float y[16];
+    float ml = -INFINITY, ydy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      lg[k] = -INFINITY; y[k] = 0.f;
+      if (k < K) {
+        lg[k] = __ldcg(prm.logits + row * K + k);
+        y[k] = __ldcg(prm.y_f32 + row * K + k);
+        ml = fmaxf(ml, lg[k]);
+        ydy += y[k] * g[k];
+      }
+    }
+    float sl = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) sl += expf(lg[k] - ml);
+    const float lse = ml + logf(sl);
+    float plogp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) { lg[k] -= lse; plogp += expf(lg[k]) * lg[k]; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) o[k] = __bfloat162float(__float2bfloat16_rn(y[k] * (g[k] - ydy) * prm.inv_T + expf(lg[k]) * (lg[k] - plogp) * prm.inv_bg));
+    uint4* dst = reinterpret_cast<uint4*>(prm.dlogits + row * prm.ld_out);
+    dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (prm.ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float t = warp_sum(o[k]);
+    if ((threadIdx.x & 31) == 0 && k < K && t != 0.f) atomicAdd(scs + k, t);
+  }
+}
+
 // The epilogue warps' share of one job.  `it` counts the tiles this CTA has processed since the
 // start of the kernel (accumulator buffer = it & 1).
 //
@@ -196,7 +282,10 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
   uint64_t* const op_bar = S.op_bar + e;
   const int gw = J.gw;
   int cs_n0 = -1;
-  if (cs_dst) { for (int i = et; i < 256; i += EPI_WARPS * 32) scs_all[i] = 0.f; }
+  float fuse_acc = 0.f;                                  // fused y head: sum p log p (forward) of this thread's rows
+  bool fuse_bwd = false;
+  if constexpr (KIND == EK_STORE_F32) fuse_bwd = J.fuse == EK_ROWS_Y_BWD;   // its bias-gradient sums use the CTA accumulator
+  if (cs_dst || fuse_bwd) { for (int i = et; i < 256; i += EPI_WARPS * 32) scs_all[i] = 0.f; }
   auto cs_flush = [&]() {
     for (int i = et; i < BN; i += EPI_WARPS * 32) {
       const float v = scs_all[i];
@@ -263,6 +352,25 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
 #pragma unroll
         for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
         ctx.sbias = sbias + ci * CW;
+        if constexpr (KIND == EK_STORE_F32) {
+          if (J.fuse != 0) {
+            // N <= 16: the lane holds the whole row -- the y head runs right here, no extra job / launch / dependency stage
+            float lg[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) lg[i] = fmaf(v[i], epi.scale, sbias[i]);
+            if (J.fuse == EK_ROWS_Y_FWD) {
+              if (mvalid) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i)
+                  if (i < N) epi.out[(int64_t)m * epi.ld + i] = lg[i];            // logits: read again by the backward head
+              }
+              fuse_acc += y_head_fwd_row(lg, *reinterpret_cast<const RowsYFwd*>(J.epi2), (int64_t)m, mvalid);
+            } else {
+              y_head_bwd_row(lg, *reinterpret_cast<const RowsYBwd*>(J.epi2), (int64_t)m, mvalid, scs_all);
+            }
+            continue;
+          }
+        }
         typename Epi::template Pre<CW> pre;
         epi.template row<CW>(m, n, v, min(CW, N - n), mvalid, pre, ctx);
       }
@@ -420,6 +528,9 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     }
     tc_fence_before();
     if (tr) trace[16 * it + 9] = clock64();
+    if constexpr (KIND == EK_STORE_F32) {
+      if (J.fuse != 0) fence_proxy_async_global();   // the fused head's bf16 rows are read through TMA by later jobs
+    }
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&S.tmem_empty_bar[as]);
@@ -433,6 +544,18 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     if (tr) trace[16 * it + 10] = clock64();
   }
   epi.finish_warp();
+  if constexpr (KIND == EK_STORE_F32) {
+    if (J.fuse == EK_ROWS_Y_FWD) {
+      const RowsYFwd& yp = *reinterpret_cast<const RowsYFwd*>(J.epi2);
+      const float sacc = warp_sum(fuse_acc);
+      if (lane == 0 && sacc != 0.f) acc_add(yp.acc, ACC_NENT, sacc * yp.inv_bg);
+    } else if (J.fuse == EK_ROWS_Y_BWD) {
+      const RowsYBwd& yp = *reinterpret_cast<const RowsYBwd*>(J.epi2);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (et < yp.K && yp.db && scs_all[et] != 0.f) atomicAdd(yp.db + et, scs_all[et]);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    }
+  }
   if (cs_dst && cs_n0 >= 0) {
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     cs_flush();
@@ -454,9 +577,14 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
   const int et = (int)threadIdx.x - 64;                 // 0 .. 511
   constexpr int NT = EPI_WARPS * 32;
   float red_acc = 0.f;                                   // kl / nent partial of this thread over the job's tiles
-  float cs[16];                                          // column-sum partials (bias gradients) of this thread
+  float cs[16];                                          // column-sum partials (bias gradients) of this thread (z head)
 #pragma unroll
   for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+  if constexpr (KIND == EK_ROWS_Y_BWD) {                 // the y head accumulates its column sums in the CTA accumulator as it goes
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    for (int i = et; i < 256; i += NT) S.scs_all[i] = 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  }
   for (int l = first; l < J.total_tiles; l += G) {
     const int mb = l, m0 = mb * BLOCK_M;
     const int rows = min(BLOCK_M, M - m0);
@@ -535,78 +663,22 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
         }
       }
     } else if constexpr (KIND == EK_ROWS_Y_FWD) {
-      const int K = prm.K;
-      if (et < rows) {
-        const int row = m0 + et;
-        float lg[16], a[16];
-        float ml = -INFINITY, ma = -INFINITY;
+      if (et < BLOCK_M) {                                   // warps 0-3, whole warps
+        const int64_t row = m0 + et;
+        const bool valid = et < rows;
+        float lg[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          lg[k] = -INFINITY; a[k] = -INFINITY;
-          if (k < K) {
-            lg[k] = __ldcg(prm.logits + (int64_t)row * K + k);
-            a[k] = (lg[k] - logf(-logf(__ldcg(prm.u + (int64_t)row * K + k)))) * prm.inv_T;
-          }
-          ml = fmaxf(ml, lg[k]); ma = fmaxf(ma, a[k]);
-        }
-        float sl = 0.f, sa = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < K) { a[k] = expf(a[k] - ma); sl += expf(lg[k] - ml); sa += a[k]; }
-        const float lse = ml + logf(sl), inv_sa = 1.f / sa;
-        float y[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          y[k] = 0.f;
-          if (k < K) {
-            const float logp = lg[k] - lse;
-            red_acc += expf(logp) * logp;
-            y[k] = a[k] * inv_sa;
-            prm.y_f32[(int64_t)row * K + k] = y[k];
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(prm.y_act + (int64_t)row * prm.ld_yact);
-        dst[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        if (prm.ld_yact > 8) dst[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+        for (int k = 0; k < 16; ++k) lg[k] = (valid && k < prm.K) ? __ldcg(prm.logits + row * prm.K + k) : -INFINITY;
+        red_acc += y_head_fwd_row(lg, prm, row, valid);
       }
     } else if constexpr (KIND == EK_ROWS_Y_BWD) {
-      const int K = prm.K;
-      if (et < rows) {
-        const int row = m0 + et;
-        float lg[16], y[16], g[16];
-        float ml = -INFINITY, ydy = 0.f;
+      if (et < BLOCK_M) {
+        const int64_t row = m0 + et;
+        const bool valid = et < rows;
+        float g[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          lg[k] = -INFINITY; y[k] = 0.f; g[k] = 0.f;
-          if (k < K) {
-            lg[k] = __ldcg(prm.logits + (int64_t)row * K + k);
-            y[k] = __ldcg(prm.y_f32 + (int64_t)row * K + k);
-            g[k] = __ldcg(prm.dy + (int64_t)row * K + k);
-          }
-          ml = fmaxf(ml, lg[k]);
-          ydy += y[k] * g[k];
-        }
-        float sl = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < K) sl += expf(lg[k] - ml);
-        const float lse = ml + logf(sl);
-        float plogp = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < K) { lg[k] -= lse; plogp += expf(lg[k]) * lg[k]; }
-        float o[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          o[k] = 0.f;
-          if (k < K) {
-            o[k] = __bfloat162float(__float2bfloat16_rn(y[k] * (g[k] - ydy) * prm.inv_T + expf(lg[k]) * (lg[k] - plogp) * prm.inv_bg));
-            cs[k] += o[k];
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(prm.dlogits + (int64_t)row * prm.ld_out);
-        dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-        if (prm.ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+        for (int k = 0; k < 16; ++k) g[k] = (valid && k < prm.K) ? __ldcg(prm.dy + row * prm.K + k) : 0.f;
+        y_head_bwd_row(g, prm, row, valid, S.scs_all);
       }
     }
     // release the row block: the rows are read by later jobs through TMA (async proxy) and by plain loads
@@ -622,37 +694,29 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
     const float s = warp_sum(red_acc);
     if (lane == 0 && s != 0.f) acc_add(prm.acc, KIND == EK_ROWS_Z_FWD ? ACC_KL : ACC_NENT, s * prm.inv_bg);
   }
-  if constexpr (KIND == EK_ROWS_Z_BWD || KIND == EK_ROWS_Y_BWD) {
+  if constexpr (KIND == EK_ROWS_Z_BWD) {
     // bias gradients: register partials -> CTA accumulator in shared memory -> one atomic per column
     float* const scs = S.scs_all;                        // 256 floats
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     for (int i = et; i < 256; i += NT) scs[i] = 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    if constexpr (KIND == EK_ROWS_Z_BWD) {
-      const int Z = prm.Z, j = (et % (Z >> 2)) * 4;
+    const int Z = prm.Z, j = (et % (Z >> 2)) * 4;
 #pragma unroll
-      for (int p4 = 0; p4 < 4; ++p4)
+    for (int p4 = 0; p4 < 4; ++p4)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (cs[4 * p4 + q] != 0.f) atomicAdd(scs + p4 * Z + j + q, cs[4 * p4 + q]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float t = warp_sum(cs[k]);
-        if (lane == 0 && t != 0.f) atomicAdd(scs + k, t);
-      }
+      for (int q = 0; q < 4; ++q)
+        if (cs[4 * p4 + q] != 0.f) atomicAdd(scs + p4 * Z + j + q, cs[4 * p4 + q]);
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    for (int col = et; col < 4 * Z; col += NT) {
+      const int p4 = col / Z, jj = col % Z;
+      const float t = scs[col];
+      if (t != 0.f && (p4 < 2 || prm.prior_mode == 2)) atomicAdd((p4 < 2 ? prm.db_enc : prm.db_prior) + (p4 & 1) * Z + jj, t);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    if constexpr (KIND == EK_ROWS_Z_BWD) {
-      const int Z = prm.Z;
-      for (int col = et; col < 4 * Z; col += NT) {
-        const int p4 = col / Z, jj = col % Z;
-        const float t = scs[col];
-        if (t != 0.f && (p4 < 2 || prm.prior_mode == 2)) atomicAdd((p4 < 2 ? prm.db_enc : prm.db_prior) + (p4 & 1) * Z + jj, t);
-      }
-    } else {
-      if (et < prm.K && scs[et] != 0.f && prm.db) atomicAdd(prm.db + et, scs[et]);
-    }
+  }
+  if constexpr (KIND == EK_ROWS_Y_BWD) {
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    if (et < prm.K && S.scs_all[et] != 0.f && prm.db) atomicAdd(prm.db + et, S.scs_all[et]);
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
   }
 }
