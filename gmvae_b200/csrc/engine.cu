@@ -122,6 +122,10 @@ struct LinView {
 
 enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8, DBG_BN128 = 16, DBG_NO_FUSED_COLSUM = 32,
        DBG_NO_PDL = 128, DBG_NO_CHAIN = 512, DBG_NO_ROW_JOBS = 1024, DBG_NO_SPREAD = 4096, DBG_NO_FUSE_HEADS = 16384,
+       DBG_COMM_OVERLAP = 32768 /* data parallel: all-reduce the gradient buffer in three buckets on a side stream while the backward
+                                   pass is still running (the chained kernel is cut at the bucket boundaries, GMVAE_COMM_SMS SMs are left
+                                   to NCCL).  Measured SLOWER than one in-stream all-reduce after a single chained launch (cfg4 per GPU, N=2: 0.536 vs
+                                   0.467 ms, N=8: 0.591 vs 0.497 ms): the cuts cost more than the overlap hides.  Off by default. */,
        DBG_ROW_JOBS = 8192 /* force the distribution heads to run as row jobs of the chained kernel (the whole forward + backward
                               pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
                               vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
@@ -1484,7 +1488,7 @@ static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st) {
   const gmvae_config& c = h->cfg;
   int64_t n = h->n_params;
   // after a cross-stream join (data-parallel all-reduce) the kernel is launched with a full dependency
-  const bool pdl = !(h->comm && h->world > 1);
+  const bool pdl = !(h->comm && h->world > 1 && (h->debug_flags & DBG_COMM_OVERLAP));
   // one launch: parameter update, the bf16 operand copies of the weight matrices, global_step += 1
   GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n / 4 + 255) / 256 + 1)), dim3(256), 0, st, pdl, h->params, (const float*)h->grads,
                          h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, h->state,
@@ -1538,7 +1542,7 @@ int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int ran
   // The persistent GEMM kernels occupy every SM they are given (one ~210 KB CTA each), which would
   // starve the all-reduce running on the side stream.  Under data parallelism a few SMs are left to
   // NCCL and NCCL is told to use no more channels (= CTAs) than that.
-  if (world_size > 1) {
+  if (world_size > 1 && (h->debug_flags & DBG_COMM_OVERLAP)) {
     const char* env = getenv("GMVAE_COMM_SMS");
     int reserve = env ? atoi(env) : 8;
     tc::g_reserved_sms = std::max(0, std::min(64, reserve));
@@ -1577,7 +1581,7 @@ int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
 
 int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps, const float* gumbel_u,
                      float* loss_terms, void* stream) {
-  h->overlap_comm = h->comm != nullptr && h->world > 1;
+  h->overlap_comm = h->comm != nullptr && h->world > 1 && (h->debug_flags & DBG_COMM_OVERLAP);
   int r = gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream);
   if (r == 0) r = gmvae_allreduce_grads(h, stream);
   h->overlap_comm = false;
