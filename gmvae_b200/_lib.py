@@ -57,6 +57,7 @@ SYMBOLS = {
     "gmvae_encode": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "gmvae_decode": (_I, [_P, _P, _I, _P, _P]),
     "gmvae_prior_table": (_I, [_P, _P, _P, _P]),
+    "gmvae_binarize": (_I, [_P, _P, _I64, _P, _I, C.c_uint64, _P, _P]),
     "gmvae_debug_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "gmvae_debug_noise": (_I, [_P, _P, _I64, _P, _I64, _P]),
     "gmvae_debug_chain_trace": (_I, [_P, _P, _I]),

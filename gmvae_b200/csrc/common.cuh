@@ -124,16 +124,26 @@ __device__ __forceinline__ float acc_total(const float* acc, int term) {
 }
 
 // ----------------------------------------------------------------------------- Philox4x32-10
+// (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the Random123 known-answer vectors are checked
+// through the host build of this struct, tests/test_input_cpu.py.)  __host__ __device__ so that the same source is
+// exercised on the CPU by the tests; the device code is the `__CUDA_ARCH__` branch.
 struct Philox {
-  __device__ static __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  __host__ __device__ static __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+  }
+  __host__ __device__ static __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t hi0 = mulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = mulhi(M1, c[2]), lo1 = M1 * c[2];
     uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
   }
   // 4 random words for (seed, stream, counter)
-  __device__ static __forceinline__ void gen(uint64_t seed, uint64_t stream, uint64_t ctr, uint32_t (&out)[4]) {
+  __host__ __device__ static __forceinline__ void gen(uint64_t seed, uint64_t stream, uint64_t ctr, uint32_t (&out)[4]) {
     uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -146,6 +156,6 @@ struct Philox {
 };
 // uniform in (0,1): never 0, never 1.  (r>>9)+0.5 is exact in fp32 (23 bits + half), so the
 // largest value is 1 - 2^-24 and the smallest 2^-24.
-__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+__host__ __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 }  // namespace gmvae

@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_chain.cuh"
 #include "kernels.cuh"
+#include "input.cuh"
 
 namespace gmvae {
 
@@ -1688,6 +1689,28 @@ int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int6
   if (q == 0) return 0;
   GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, eps, n_eps, u, n_u,
                          (const DeviceState*)h->state, (uint64_t)h->rank));
+  return 0;
+}
+
+// runners.create_dataset._preprocess (runners.py:44-47) on the device: x = (intensity / 255 < uniform).
+// `intensities` [n_rows, D] bytes resident in HBM; output row r comes from row row_index[r] (device int64[batch],
+// each in [0, n_rows)) or, without an index, from row r.  Uniforms: Philox keyed by (seed, draw, rank, element).
+int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, const int64_t* row_index, int batch, uint64_t draw,
+                   uint8_t* x_u8, void* stream) {
+  GM_REQUIRE(h && h->state, "null handle");
+  GM_REQUIRE(batch >= 0 && n_rows >= 0, "negative size");
+  if (batch == 0) return 0;
+  GM_REQUIRE(intensities && x_u8, "null argument");
+  GM_REQUIRE(row_index || batch <= n_rows, "batch exceeds the number of intensity rows");
+  const int D = h->cfg.data_size;
+  const uint8_t* lo = intensities; const uint8_t* hi = intensities + n_rows * D;
+  GM_REQUIRE(x_u8 + (int64_t)batch * D <= lo || x_u8 >= hi, "x_u8 must not overlap the intensities");
+  const int64_t n_out = (int64_t)batch * D, n_quads = (n_out + 3) / 4;
+  const int vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(intensities) | reinterpret_cast<uintptr_t>(x_u8)) & 3) == 0;
+  const int blocks = (int)std::min<int64_t>((n_quads + 255) / 256, 8 * tc::num_sms());
+  GM_CHECK_CUDA(launch_k(binarize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, false, intensities, row_index, D, n_out,
+                         (const unsigned long long*)&h->state->seed, draw, (uint64_t)h->rank, vec, x_u8));
+  h->launches++;
   return 0;
 }
 

@@ -186,6 +186,35 @@ class Engine:
                                              self._stream()), "gmvae_train_step")
         return self.loss_buf
 
+    # ------------------------------------------------------------------ input pipeline on the device
+    def binarize(self, intensities: torch.Tensor, batch: Optional[int] = None, first_row: int = 0,
+                 row_index: Optional[torch.Tensor] = None, draw: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Dynamic binarisation of runners.create_dataset._preprocess (runners.py:44-47), `intensity/255 < uniform`,
+        on device-resident bytes `intensities` [N, D].  Rows `first_row .. first_row+batch` (the reference's
+        contiguous batches) or the rows named by `row_index` (int64 CUDA tensor).  Returns uint8 {0,1} [batch, D]."""
+        if intensities.dtype != torch.uint8 or not intensities.is_cuda or not intensities.is_contiguous() or intensities.dim() != 2:
+            raise ValueError("intensities must be a contiguous uint8 CUDA tensor [N, D]")
+        N, D = intensities.shape
+        if D != self.data_size:
+            raise ValueError(f"expected {self.data_size} features, got {D}")
+        if row_index is not None:
+            if row_index.dtype != torch.int64 or not row_index.is_cuda or not row_index.is_contiguous():
+                raise ValueError("row_index must be a contiguous int64 CUDA tensor")
+            B, src, n_rows = int(row_index.numel()), intensities, N
+        else:
+            B = int(N - first_row if batch is None else batch)
+            if first_row < 0 or B < 0 or first_row + B > N:
+                raise ValueError(f"rows [{first_row}, {first_row + B}) outside the {N} intensity rows")
+            src, n_rows = intensities[first_row:], N - first_row
+        if out is None:
+            out = torch.empty(B, D, dtype=torch.uint8, device=self.device)
+        elif out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous() or tuple(out.shape) != (B, D):
+            raise ValueError("out must be a contiguous uint8 CUDA tensor [batch, D]")
+        self._keep_in = [intensities, row_index, out]
+        _lib.check(self.lib.gmvae_binarize(self._h, src.data_ptr(), n_rows, _ptr(row_index), B, int(draw) & (2 ** 64 - 1),
+                                           out.data_ptr(), self._stream()), "gmvae_binarize")
+        return out
+
     # ------------------------------------------------------------------ forward-only helpers
     def encode(self, x, eps=None, gumbel_u=None):
         """(logits_y or None, z_mean, z_sample): encoder side of the forward pass (gmvae.py:140-150, vae.py:105-112)."""

@@ -1,6 +1,7 @@
 """Command line -- same flags, defaults and `--flag=value` syntax as
-/root/reference/scripts/run_gmvae.py:11-58 (tf.app.flags), plus three additive flags
-(`--precision`, `--objective`, and torchrun-based data parallelism needs none).
+/root/reference/scripts/run_gmvae.py:11-58 (tf.app.flags), plus additive flags (`--precision`,
+`--objective`, `--dataset_path`, `--image_summaries`).  Data parallelism needs no flag: launch with
+`torchrun --nproc-per-node N -m gmvae_b200.run_gmvae ...` and `--batch_size` is the per-GPU batch.
 
     python -m gmvae_b200.run_gmvae --mode=train --model=gmvae --latent_size=64 --hidden_size=512 \
         --num_layers=2 --batch_size=100 --max_steps=200
@@ -39,6 +40,10 @@ def build_parser() -> argparse.ArgumentParser:
     # Additive flags (no reference counterpart)
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="GEMM path: tcgen05 bf16 or fp32 validation.")
     p.add_argument("--objective", default="reference", choices=["reference", "marginal"], help="See DESIGN.md section 1.")
+    p.add_argument("--dataset_path", default=None, help="Directory with the MNIST IDX files (plain or .gz) or mnist.npz; "
+                   "default $GMVAE_MNIST_DIR, else a synthetic stand-in (the reference downloads through TFDS).")
+    p.add_argument("--image_summaries", type=int, default=1, help="Write the input / reconstruction / sample tiles with "
+                   "every summary (the reference always does).")
     return p
 
 

@@ -149,6 +149,19 @@ GMVAE_API int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, cons
 GMVAE_API int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* stream);
 GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream);
 
+/* Input pipeline on the device = runners.create_dataset._preprocess (runners.py:44-47):
+ *     image = cast(image, float32) / 255. ;  image = image < random.uniform(shape(image))
+ * (dynamic, inverted binarisation: a pixel is 1 with probability 1 - intensity).
+ *   intensities [n_rows, data_size] bytes 0..255, device-resident (MNIST train = 47 MB)
+ *   row_index   device int64[batch], each in [0, n_rows): source row of every output row, or NULL
+ *               = rows 0..batch-1 of `intensities` (pass `intensities + first_row * data_size` for a
+ *               contiguous batch: the reference batches first and shuffles batches, runners.py:50-57)
+ *   draw        counter of this draw (e.g. the global step); uniforms are Philox4x32-10 keyed by
+ *               (seed, draw, rank, element), 24-bit, open interval (0,1), never stored
+ *   x_u8        [batch, data_size] bytes in {0,1}: what gmvae_forward_backward / gmvae_train_step take */
+GMVAE_API int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, const int64_t* row_index,
+                   int batch, uint64_t draw, uint8_t* x_u8, void* stream);
+
 /* Kernel-level test hook: C[M,N] = A[M,K] * B[K,N] through the same GEMM kernels the step
  * uses (impl 0 = fp32 SIMT, 1 = tcgen05 bf16).  A, B, C are device float arrays, row-major;
  * transA/transB say the stored matrix is the transpose ([K,M] / [N,K]).  Used by tests/. */
