@@ -84,11 +84,11 @@ def load_mnist(dataset_path: Optional[str], split: str) -> Optional[Tuple[np.nda
 
 
 def synthetic_mnist(split: str, num_examples: Optional[int] = None, data_size: int = 784) -> Tuple[np.ndarray, np.ndarray]:
-    """Stand-in with MNIST's tensor contract: ten smooth class prototypes plus per-example jitter, uint8
-    intensities [N, data_size], labels int64 [N].  Deterministic per split."""
+    """Stand-in with MNIST's tensor contract: ten class prototypes (shared by the splits, like digits) plus
+    per-example jitter, uint8 intensities [N, data_size], labels int64 [N].  Deterministic per split."""
     n = int(num_examples or SPLIT_SIZES[split])
-    rng = np.random.default_rng(1234 if split == "train" else 4321)
-    protos = rng.random((10, data_size)) ** 3                      # mostly dark, a few bright pixels, like digits
+    protos = np.random.default_rng(1234).random((10, data_size)) ** 3     # mostly dark, a few bright pixels
+    rng = np.random.default_rng(2345 if split == "train" else 4321)
     labels = rng.integers(0, 10, size=n).astype(np.int64)
     jitter = rng.random((n, 1)) * 0.4 + 0.6
     images = np.clip(protos[labels] * jitter * 255.0 + 0.5, 0, 255).astype(np.uint8)
