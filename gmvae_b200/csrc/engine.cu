@@ -158,6 +158,7 @@ struct gmvae_handle {
   std::vector<ShadowEntry> shadow_host;
   ShadowEntry* shadow_dev = nullptr; int shadow_tiles = 0;
   DeviceState* state = nullptr;
+  uint64_t seed_host = 0;                // host copy of state->seed (it changes only through gmvae_set_seed)
   int64_t launches = 0;
   int debug_flags = 0;
   // per-launch CUDA-event profile (off by default; bench.py turns it on for a few eager steps)
@@ -1396,6 +1397,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
   DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull; s0.adam_blocks = 0; s0.pad = 0;
+  h->seed_host = s0.seed;
   GM_CHECK_CUDA(cudaMemcpy(h->state, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   *out = h;
   return 0;
@@ -1523,6 +1525,7 @@ int gmvae_set_seed(gmvae_handle* h, uint64_t seed) {
   GM_REQUIRE(h, "null argument");
   unsigned long long v = seed;
   GM_CHECK_CUDA(cudaMemcpy(&h->state->seed, &v, sizeof(v), cudaMemcpyHostToDevice));
+  h->seed_host = seed;
   return 0;
 }
 
@@ -1705,11 +1708,19 @@ int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, 
   const int D = h->cfg.data_size;
   const uint8_t* lo = intensities; const uint8_t* hi = intensities + n_rows * D;
   GM_REQUIRE(x_u8 + (int64_t)batch * D <= lo || x_u8 >= hi, "x_u8 must not overlap the intensities");
-  const int64_t n_out = (int64_t)batch * D, n_quads = (n_out + 3) / 4;
-  const int vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(intensities) | reinterpret_cast<uintptr_t>(x_u8)) & 3) == 0;
-  const int blocks = (int)std::min<int64_t>((n_quads + 255) / 256, 8 * tc::num_sms());
-  GM_CHECK_CUDA(launch_k(binarize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, false, intensities, row_index, D, n_out,
-                         (const unsigned long long*)&h->state->seed, draw, (uint64_t)h->rank, vec, x_u8));
+  const int64_t n_out = (int64_t)batch * D;
+  const int mode = binarize_mode(intensities, x_u8, D);
+  const int64_t units = mode == BINARIZE_VEC16 ? n_out / 16 : (n_out + 3) / 4;      // work items of one thread-iteration
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    GM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, binarize_kernel, BINARIZE_THREADS, 0));
+    blocks_per_sm = std::max(1, blocks_per_sm);
+  }
+  const int blocks = (int)std::min<int64_t>((units + BINARIZE_THREADS - 1) / BINARIZE_THREADS, (int64_t)blocks_per_sm * tc::num_sms());
+  PhiloxKeys rk;                                                                       // uniforms keyed by (seed, draw, rank, element)
+  philox_schedule(binarize_key(h->seed_host, draw), rk);
+  GM_CHECK_CUDA(launch_k(binarize_kernel, dim3(blocks), dim3(BINARIZE_THREADS), 0, (cudaStream_t)stream, false, intensities, row_index, D,
+                         n_out, rk, (uint64_t)h->rank, mode, x_u8));
   h->launches++;
   return 0;
 }

@@ -83,7 +83,13 @@ def host_lib(tmp_path_factory):
     lib.host_u01.argtypes = [C.c_uint32]
     lib.host_u01.restype = C.c_float
     lib.host_binarize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
-    lib.host_binarize.restype = None
+    lib.host_binarize.restype = C.c_int
+    lib.host_threshold_agrees.argtypes = [C.c_uint32, C.c_uint32]
+    lib.host_threshold_agrees.restype = C.c_int
+    lib.host_threshold.argtypes = [C.c_uint32]
+    lib.host_threshold.restype = C.c_uint32
+    lib.host_philox_scheduled.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.host_philox_scheduled.restype = None
     return lib
 
 
@@ -98,33 +104,83 @@ def test_kernel_source_philox_known_answers(host_lib):
         assert np.float32(host_lib.host_u01(r)) == O.u01(np.array([r], dtype=np.uint32))[0]
 
 
-def _run_host(lib, inten, row_index, batch, seed, draw, rank, vec):
+def test_kernel_source_scheduled_philox_and_threshold_table(host_lib):
+    """The kernel's two shortcuts are exact: Philox with the key schedule expanded on the host equals Philox::gen, and
+    `(r >> 9) >= T[v]` equals the reference's `float32(v) / 255 < uniform` (runners.py:45-46) -- checked at the two
+    uniforms around every threshold, at the extremes and at random words."""
+    for ctr, key, want in PHILOX_KAT:
+        out = (C.c_uint32 * 4)()
+        host_lib.host_philox_scheduled(key[0] | (key[1] << 32), ctr[2] | (ctr[3] << 32), ctr[0] | (ctr[1] << 32), out)
+        assert tuple(out) == want
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        seed, stream, ctr = (int(x) for x in rng.integers(0, 2 ** 63, size=3))
+        a, b = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+        host_lib.host_philox(seed, stream, ctr, a)
+        host_lib.host_philox_scheduled(seed, stream, ctr, b)
+        assert tuple(a) == tuple(b)
+    assert host_lib.host_threshold(0) == 0 and host_lib.host_threshold(255) == 2 ** 23
+    words = [int(x) for x in rng.integers(0, 2 ** 32, size=64)]
+    for v in range(256):
+        t = host_lib.host_threshold(v)
+        assert 0 <= t <= 2 ** 23
+        probe = [0, 0xFFFFFFFF] + words
+        for m in (t - 2, t - 1, t, t + 1):
+            if 0 <= m < 2 ** 23:
+                probe += [m << 9, (m << 9) | 0x1FF]
+        assert all(host_lib.host_threshold_agrees(v, r) for r in probe), v
+    # the thresholds are the oracle's: x = 1 exactly for the uniforms above fl(v / 255)
+    v = np.arange(256, dtype=np.uint8)
+    unit = v.astype(np.float32) / np.float32(255.0)
+    T = np.array([host_lib.host_threshold(int(i)) for i in v], dtype=np.int64)
+    below = O.u01(((np.maximum(T - 1, 0)) << 9).astype(np.uint32))
+    assert (unit[T > 0] >= below[T > 0]).all()
+    at = O.u01((np.minimum(T, 2 ** 23 - 1) << 9).astype(np.uint32))
+    assert (unit[T < 2 ** 23] < at[T < 2 ** 23]).all()
+
+
+def _run_host(lib, inten, row_index, batch, seed, draw, rank, mode):
     D = inten.shape[1]
     out = np.full((batch, D), 0xEE, dtype=np.uint8)
     idx = None if row_index is None else np.ascontiguousarray(row_index, dtype=np.int64)
-    lib.host_binarize(inten.ctypes.data, None if idx is None else idx.ctypes.data, D, batch * D, seed, draw, rank, int(vec),
-                      out.ctypes.data)
+    used = lib.host_binarize(inten.ctypes.data, None if idx is None else idx.ctypes.data, D, batch * D, seed, draw, rank, int(mode),
+                             out.ctypes.data)
+    assert used == mode or mode < 0
     return out
 
 
-@pytest.mark.parametrize("D,batch,vec", [(784, 33, True), (784, 33, False), (10, 7, False), (3, 5, False), (8, 1, True)])
-def test_kernel_source_matches_oracle(host_lib, D, batch, vec):
+BYTES, VEC4, VEC16 = 0, 1, 2
+
+
+@pytest.mark.parametrize("D,batch,mode", [(784, 33, VEC16), (784, 33, VEC4), (784, 33, BYTES), (10, 7, BYTES), (3, 5, BYTES),
+                                          (8, 1, VEC4), (16, 1, VEC16), (48, 257, VEC16), (20, 19, VEC4)])
+def test_kernel_source_matches_oracle(host_lib, D, batch, mode):
     rng = np.random.default_rng(D * 1000 + batch)
     n_rows = batch + 9
     inten = rng.integers(0, 256, size=(n_rows, D), dtype=np.uint8)
     seed, draw, rank = 0x243F6A8885A308D3, 12345, 3
-    got = _run_host(host_lib, inten, None, batch, seed, draw, rank, vec)
+    got = _run_host(host_lib, inten, None, batch, seed, draw, rank, mode)
     assert (got == O.binarize(inten, None, batch, seed, draw, rank)).all()
     idx = rng.integers(0, n_rows, size=batch)                              # gathered rows, repeats allowed
-    got = _run_host(host_lib, inten, idx, batch, seed, draw, rank, vec)
+    got = _run_host(host_lib, inten, idx, batch, seed, draw, rank, mode)
     assert (got == O.binarize(inten, idx, batch, seed, draw, rank)).all()
     assert set(np.unique(got)) <= {0, 1}
 
 
-def test_kernel_source_all_intensities(host_lib):
-    # every byte value against many uniforms: the IEEE division and the comparison agree everywhere
+def test_kernel_source_all_intensities_and_mode_choice(host_lib):
+    # every byte value against many uniforms, on every path
     inten = np.tile(np.arange(256, dtype=np.uint8), (64, 1))               # D = 256
-    got = _run_host(host_lib, inten, None, 64, 99, 1, 0, True)
     want = O.binarize(inten, None, 64, 99, 1, 0)
-    assert (got == want).all()
-    assert (got[:, 0] == 1).all() and (got[:, 255] == 0).all()
+    for mode in (BYTES, VEC4, VEC16):
+        got = _run_host(host_lib, inten, None, 64, 99, 1, 0, mode)
+        assert (got == want).all()
+        assert (got[:, 0] == 1).all() and (got[:, 255] == 0).all()
+    # the widest path the shapes and alignments allow is the one chosen
+    buf = np.zeros(64 * 48 + 64, dtype=np.uint8)
+    base = (-buf.ctypes.data) % 16
+    out = np.zeros(64 * 48 + 64, dtype=np.uint8)
+    obase = (-out.ctypes.data) % 16
+    for off, D, want_mode in ((0, 48, VEC16), (4, 48, VEC4), (1, 48, BYTES), (0, 20, VEC4), (0, 10, BYTES)):
+        src = buf[base + off:]
+        used = host_lib.host_binarize(src.ctypes.data, None, D, 4 * D, 1, 2, 0, -1, out[obase:].ctypes.data)
+        assert used == want_mode, (off, D, used)
