@@ -278,6 +278,21 @@ def run_gpu_arm(args, w):
                 for k, v in eng.profile_read().items()}
         eng.profile(False)
 
+        # ---- input pipeline kernel: dynamic binarisation of one batch of device-resident intensities ----
+        inten = torch.randint(0, 256, (B, D), dtype=torch.uint8, device=dev)
+        x_bin = torch.empty_like(x_dev)
+        for i in range(3):
+            eng.binarize(inten, out=x_bin, draw=i)
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+        for i, (a, b) in enumerate(evb):
+            flush_l2(l2_buf)
+            a.record(side)
+            eng.binarize(inten, out=x_bin, draw=3 + i)
+            b.record(side)
+        side.synchronize()
+        bin_ms = sorted(a.elapsed_time(b) for a, b in evb)[len(evb) // 2]
+        del inten, x_bin
+
         # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ----------------
         copy_stream = torch.cuda.Stream(dev)
         stage = [torch.empty_like(x_dev) for _ in range(2)]
@@ -350,6 +365,10 @@ def run_gpu_arm(args, w):
                      "peak_source": peak_src, "flop_per_sample": fps, "tc_flop_per_sample": tc_flops_per_sample(w, args.objective),
                      "whole_step_tflops": step_tf, "whole_step_frac": step_tf / peak_tf},
         "kernel_profile": prof,
+        "input_pipeline": {"kernel": "binarize_kernel (runners.py:44-47 on device-resident intensities; not part of the timed step)",
+                           "bound": "hbm", "achieved": 2.0 * B * D / (bin_ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                           "frac": 2.0 * B * D / (bin_ms * 1e-3) / 1e9 / peak_hbm, "ms_per_batch": bin_ms,
+                           "samples_per_s": B / (bin_ms * 1e-3), "bytes_per_sample": 2 * D},
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

@@ -51,6 +51,10 @@ def main(argv=None):
     flags = build_parser().parse_args(argv)
     if flags.mode == "train":
         runners.run_train(flags)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():         # torchrun: leave together
+            dist.barrier()
+            dist.destroy_process_group()
     elif flags.mode == "eval":
         runners.run_eval(flags)
 

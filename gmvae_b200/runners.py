@@ -134,9 +134,10 @@ def run_train(config):
         eng.init_data_parallel()
     logdir = logdir_for(config)
     if not os.path.exists(logdir):
-        print("Creating log directory at {}".format(logdir))
+        if rank == 0:
+            print("Creating log directory at {}".format(logdir))
         os.makedirs(logdir, exist_ok=True)
-    if utils.restore_checkpoint_if_exists(eng, logdir):               # MonitoredTrainingSession auto-restore (:222-225)
+    if utils.restore_checkpoint_if_exists(eng, logdir) and rank == 0:  # MonitoredTrainingSession auto-restore (:222-225)
         print(f"Restored checkpoint of step {eng.global_step} from {logdir}")
     cur_step = eng.global_step
     batches = create_dataset(config, "train", shuffle=True, repeat=True, engine=eng, world=world, rank=rank,
