@@ -390,3 +390,65 @@ def test_run_eval_loop_and_outputs(tmp_path, monkeypatch):
     ks = [c for c in model.calls if c[2] is not None]
     assert len(ks) == 1 and ks[0][1] == 100 and len(ks[0][2]) == 1 and 0 <= ks[0][2][0] < 10    # runners.py:283-286
     assert eng.draws == [0, 1, 2]                                      # one pass, no shuffle, no repeat
+
+
+# ---------------------------------------------------------------------------- run_train under torchrun (world size 2, gloo)
+def _dp_worker(rank, world, port, logroot):
+    import torch.distributed as dist
+    from gmvae_b200 import dist as dist_mod
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank))
+    os.environ.pop("GMVAE_MNIST_DIR", None)
+    torch.set_num_threads(1)
+
+    class DPEngine(FakeEngine):
+        """Like the native step under data parallelism: the loss every rank reads is the all-reduced one."""
+        rows_seen = []
+
+        def init_data_parallel(self):
+            self.world_size, self.rank = dist.get_world_size(), dist.get_rank()
+
+        def binarize(self, intensities, batch=None, first_row=0, row_index=None, draw=0, out=None):
+            self.rows_seen.append((first_row, batch))
+            return super().binarize(intensities, batch=batch, first_row=first_row, draw=draw)
+
+        def train_step(self, x, eps=None, gumbel_u=None, global_batch=None):
+            t = super().train_step(x, global_batch=global_batch)
+            t = t + float(self.rank)                                   # a rank-dependent local term ...
+            dist.all_reduce(t)                                         # ... summed over ranks, as the gradient buffer's tail is
+            return t / world
+
+    eng = DPEngine(lambda s: 500.0 - min(s, 30))
+    runners.create_model = lambda config, data_dim: FakeModel()
+    runners._configure = lambda m, config, device: eng
+    dist_mod.init_process_group = lambda backend="nccl": dist.init_process_group("gloo", rank=rank, world_size=world)
+    data.SPLIT_SIZES = {"train": 1000, "test": 100}
+    cfg = types.SimpleNamespace(mode="train", model="gmvae", latent_size=4, hidden_size=8, num_layers=1, mixture_components=10,
+                                batch_size=50, logdir=logroot, random_seed=4, learning_rate=1e-3, max_steps=10 ** 6,
+                                early_stop_rounds=40, early_stop_threshold=0.001, summarise_every=25, gpu_id="0", gpu_num="0",
+                                dataset_path=None, image_summaries=0)
+    runners.run_train(cfg)
+    torch.save({"step": eng.global_step, "rows": eng.rows_seen, "gb": sorted(set(eng.global_batches))}, os.path.join(logroot, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_run_train_world_size_2_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    logroot = str(tmp_path / "dp")
+    os.makedirs(logroot)
+    mp.spawn(_dp_worker, args=(2, port, logroot), nprocs=2, join=True)
+    r0, r1 = torch.load(os.path.join(logroot, "rank0.pt")), torch.load(os.path.join(logroot, "rank1.pt"))
+    # both ranks stopped at the same step: the loss they replay through the hook is the all-reduced one.
+    # flat from step 31: steps 31..70 are 40 stale calls -> requested at 70, noticed at the end of that window (75)
+    assert r0["step"] == r1["step"] == 75
+    assert r0["gb"] == r1["gb"] == [100]                               # divisor of the batch means = world * batch_size
+    # every global batch of 100 rows is split into two contiguous halves, rank order
+    assert len(r0["rows"]) == len(r1["rows"]) == 75
+    for (f0, n0), (f1, n1) in zip(r0["rows"], r1["rows"]):
+        assert n0 == n1 == 50 and f1 == f0 + 50 and f0 % 100 == 0
+    logdir = os.path.join(logroot, "gmvae", "h8_n1_z4")
+    recs = [json.loads(l) for l in open(os.path.join(logdir, "summaries.jsonl"))]
+    assert [r["step"] for r in recs] == [25, 50, 75]                   # written once (rank 0 only)
+    assert utils.get_checkpoint_state(logdir)["all_model_checkpoint_paths"] == ["model.ckpt-75"]
