@@ -184,6 +184,10 @@ def run_reference_arm(args, w):
     nsteps = max(1, min(args.steps, int(60.0 / max(dt1 / 2, 1e-4))))
     rate, dt = cpu_step_rate(w, sample, nsteps, cores)
     args.steps = nsteps
+    # the reference's own session config pins TF to one intra-op and one inter-op thread (runners.py:203-204):
+    # the same step on ONE thread, a bounded sample, reported beside the all-cores number
+    one_steps = max(1, min(3, int(10.0 / max(dt / max(nsteps, 1) * cores * 0.5, 1e-3))))
+    rate1, dt1t = cpu_step_rate(w, sample, one_steps, 1)
     line = {
         "impl": "reference", "metric": "GMVAE train samples/sec (fwd+bwd+Adam)", "value": rate, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
@@ -192,6 +196,9 @@ def run_reference_arm(args, w):
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} samples/step x {args.steps} steps of the same model (restated reference graph on "
                                    f"PyTorch-CPU fp32; TF 1.13 not installable)"},
+        "cpu_baseline_single_thread": {"value": rate1, "unit": "samples/s", "cores": 1, "kind": "port",
+                                       "sample": f"{sample} samples/step x {one_steps} steps ({dt1t:.1f} s); the reference's own "
+                                                 f"ConfigProto uses intra_op = inter_op = 1 (runners.py:203-204)"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

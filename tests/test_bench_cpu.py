@@ -54,6 +54,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "cfg3" in d["config"]["workload"]
+    one = d["cpu_baseline_single_thread"]                        # the reference pins TF to one thread (runners.py:203-204)
+    assert one["cores"] == 1 and one["value"] > 0 and one["kind"] == "port"
     # the other ranks of a torchrun launch exit 0 without work and without output
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
