@@ -51,6 +51,8 @@ SYMBOLS = {
     "gmvae_nccl_unique_id": (_I, [C.c_char_p]),
     "gmvae_nccl_init": (_I, [_P, C.c_char_p, _I, _I]),
     "gmvae_allreduce_grads": (_I, [_P, _P]),
+    "gmvae_peer_export": (_I, [_P, _I, _I, C.c_char_p]),
+    "gmvae_peer_attach": (_I, [_P, C.c_char_p]),
     "gmvae_train_step": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gmvae_step_graph_capture": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gmvae_step_graph_launch": (_I, [_P, _P]),

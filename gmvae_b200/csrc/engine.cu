@@ -26,6 +26,7 @@
 #include "gemm_chain.cuh"
 #include "kernels.cuh"
 #include "input.cuh"
+#include "peer.cuh"
 
 namespace gmvae {
 
@@ -170,6 +171,12 @@ struct gmvae_handle {
   cudaEvent_t comm_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int comm_ev_next = 0;
   bool overlap_comm = false;             // set by gmvae_train_step
+  // experimental: the exchange step as our own kernels over NVLink peer memory (peer.cuh); off unless gmvae_peer_attach was called
+  bool peer_ready = false;
+  void* peer_region = nullptr;           // this rank's symmetric region (cudaMalloc, exported through cudaIpc)
+  void* peer_mapped[peer::MAX_WORLD] = {};   // other ranks' regions as mapped into this process
+  peer::Layout peer_layout;
+  peer::Peers peer_ptrs;
   int64_t reduced_upto = 0;              // floats of `grads` already handed to NCCL this step
   int64_t bucket_end[2] = {0, 0};        // flat offsets where bucket 0 (decoder) / 1 (encoder, prior) end
   int chunk_samples = 0;                 // objective M: samples per chunk of per-component rows
@@ -1406,6 +1413,8 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
 void gmvae_destroy(gmvae_handle* h) {
   if (!h) return;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (void* m : h->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
+  if (h->peer_region) cudaFree(h->peer_region);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   for (auto& e : h->comm_ev) if (e) cudaEventDestroy(e);
@@ -1563,8 +1572,65 @@ int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int ran
   for (auto& e : h->comm_ev) GM_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
+// ---- experimental: all-reduce over NVLink peer memory (peer.cuh).  export: allocate this rank's symmetric region and hand out
+// its cudaIpc handle; attach: map every rank's region (handles in rank order, own included).  The caller puts a barrier
+// between attach and the first step.
+int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]) {
+  GM_REQUIRE(h && out, "null argument");
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(world_size >= 2 && world_size <= peer::MAX_WORLD && rank >= 0 && rank < world_size, "bad world_size / rank");
+  GM_REQUIRE(!h->peer_region, "peer region already exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  const int64_t total = h->n_params + ACC_SLOTS;
+  GM_REQUIRE(total % 4 == 0, "gradient buffer length must be a multiple of 4 floats");
+  GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+  h->peer_layout = peer::make_layout(world_size, total);
+  GM_CHECK_CUDA(cudaMalloc(&h->peer_region, h->peer_layout.bytes));
+  GM_CHECK_CUDA(cudaMemset(h->peer_region, 0, h->peer_layout.bytes));
+  GM_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ipc;
+  GM_CHECK_CUDA(cudaIpcGetMemHandle(&ipc, h->peer_region));
+  memcpy(out, &ipc, 64);
+  if (h->world == 1) { h->world = world_size; h->rank = rank; }
+  GM_REQUIRE(h->world == world_size && h->rank == rank, "world_size / rank differ from the NCCL communicator's");
+  return 0;
+}
+int gmvae_peer_attach(gmvae_handle* h, const char* handles) {
+  GM_REQUIRE(h && handles, "null argument");
+  GM_REQUIRE(h->peer_region && !h->peer_ready, "call gmvae_peer_export first (once)");
+  GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+  const peer::Layout& L = h->peer_layout;
+  for (int r = 0; r < L.world; ++r) {
+    void* base = h->peer_region;
+    if (r != h->rank) {
+      cudaIpcMemHandle_t ipc;
+      memcpy(&ipc, handles + 64 * r, 64);
+      GM_CHECK_CUDA(cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_mapped[r] = base;
+    }
+    char* b = static_cast<char*>(base);
+    h->peer_ptrs.recv[r] = reinterpret_cast<float4*>(b + L.recv_off);
+    h->peer_ptrs.red[r] = reinterpret_cast<float4*>(b + L.red_off);
+    h->peer_ptrs.flags[r] = reinterpret_cast<unsigned long long*>(b + L.flags_off);
+  }
+  h->peer_ready = true;
+  return 0;
+}
+static int peer_allreduce(gmvae_handle* h, cudaStream_t st) {
+  const peer::Layout& L = h->peer_layout;
+  peer::Local* loc = reinterpret_cast<peer::Local*>(static_cast<char*>(h->peer_region) + L.local_off);
+  auto grid = [&](int64_t items) { return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((items + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()))); };
+  float4* g = reinterpret_cast<float4*>(h->grads);
+  GM_CHECK_CUDA(launch_k(peer::push_kernel, grid(L.n4), dim3(peer::THREADS), 0, st, false, (const float4*)g, L, h->rank, h->peer_ptrs, loc));
+  GM_CHECK_CUDA(launch_k(peer::reduce_kernel, grid(L.cap4), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc));
+  GM_CHECK_CUDA(launch_k(peer::gather_kernel, grid(L.n4), dim3(peer::THREADS), 0, st, false, g, L, h->rank, h->peer_ptrs, loc));
+  h->launches += 3;
+  return 0;
+}
+
 int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
   GM_TRY(check_ready(h));
+  if (h->peer_ready && h->world > 1) return peer_allreduce(h, (cudaStream_t)stream);
   if (!h->comm || h->world == 1) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = h->n_params + ACC_SLOTS;

@@ -326,6 +326,21 @@ class Engine:
         obj = [bytes(buf.raw)]
         dist.broadcast_object_list(obj, src=0)
         _lib.check(self.lib.gmvae_nccl_init(self._h, obj[0], self.world_size, self.rank), "gmvae_nccl_init")
+        import os
+        if os.environ.get("GMVAE_DP_PEER") == "1":
+            self.attach_peers()
+
+    def attach_peers(self):
+        """EXPERIMENTAL, off by default: replace the NCCL all-reduce of the step by the library's own two-shot all-reduce
+        over NVLink peer memory (csrc/peer.cuh).  Every rank exports its symmetric region, the cudaIpc handles travel
+        through torch.distributed, and a barrier separates attaching from the first step."""
+        import torch.distributed as dist
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.gmvae_peer_export(self._h, self.world_size, self.rank, buf), "gmvae_peer_export")
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, bytes(buf.raw))
+        _lib.check(self.lib.gmvae_peer_attach(self._h, b"".join(handles)), "gmvae_peer_attach")
+        dist.barrier()
 
     PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc"]
 

@@ -128,6 +128,14 @@ GMVAE_API int gmvae_nccl_unique_id(char out[128]);
 GMVAE_API int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int rank);
 GMVAE_API int gmvae_allreduce_grads(gmvae_handle* h, void* stream);
 
+/* EXPERIMENTAL (off unless attached): gmvae_allreduce_grads as the library's own kernels over NVLink peer memory --
+ * a two-shot all-reduce (reduce-scatter by push, all-gather by push; csrc/peer.cuh) in place of ncclAllReduce.
+ * export() allocates this rank's symmetric region and returns its cudaIpcMemHandle_t (64 bytes); the caller gathers
+ * the handles of all ranks (rank order, own included), passes them to attach() and puts a barrier before the first
+ * step.  One node, P2P-capable GPUs, world_size <= 16. */
+GMVAE_API int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]);
+GMVAE_API int gmvae_peer_attach(gmvae_handle* h, const char* handles);
+
 /* One whole iteration of the hot loop `sess.run([train_op, global_step])`
  * (runners.py:231-232): forward_backward -> allreduce -> finalize_loss -> adam_step.
  * capture() records it once into a CUDA graph for fixed pointers; launch() replays it. */

@@ -1,0 +1,48 @@
+"""The experimental peer-memory all-reduce (gmvae_b200/csrc/peer.cuh; off by default): its layout and element
+arithmetic, compiled for the host (tests/native/host_peer.cu) and run for `world` simulated ranks, equal a rank-ordered
+fp32 sum on every rank, bit for bit -- including ragged last shards and buffers shorter than the world size.  The
+synchronisation (system-scope flags over NVLink) is not covered here; it needs GPUs."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+@pytest.fixture(scope="module")
+def host_peer(tmp_path_factory):
+    if not (os.path.exists(NVCC) or shutil.which("nvcc")):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("host_peer") / "libhost_peer.so")
+    cmd = [NVCC if os.path.exists(NVCC) else "nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
+           "-Xcompiler", "-fPIC", os.path.join(ROOT, "tests", "native", "host_peer.cu"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lib = C.CDLL(out)
+    lib.host_peer_allreduce.argtypes = [C.c_int, C.c_longlong, C.c_void_p]
+    lib.host_peer_allreduce.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("world,n", [(2, 8), (2, 2104700), (3, 100), (8, 2104700), (8, 12), (5, 4), (16, 6070180), (1, 16)])
+def test_simulated_ranks_agree_with_rank_ordered_sum(host_peer, world, n):
+    rng = np.random.default_rng(world * 1000003 + n)
+    g = rng.standard_normal((world, n)).astype(np.float32)
+    want = g[0].copy()
+    for r in range(1, world):
+        want = want + g[r]                                             # fp32, rank order: what reduce_slots does
+    buf = np.ascontiguousarray(g.copy())
+    assert host_peer.host_peer_allreduce(world, n, buf.ctypes.data) == 0
+    for r in range(world):
+        assert (buf[r].view(np.uint32) == want.view(np.uint32)).all(), r    # identical bits on every rank
+
+
+def test_rejects_bad_shapes(host_peer):
+    buf = np.zeros((2, 6), dtype=np.float32)
+    assert host_peer.host_peer_allreduce(2, 6, buf.ctypes.data) == -1       # not a multiple of 4 floats
+    assert host_peer.host_peer_allreduce(17, 8, buf.ctypes.data) == -1
