@@ -1,4 +1,4 @@
-"""Committed golden vectors (tests/golden/*.json, written by tools/make_golden.py from the oracle).
+"""Committed golden vectors (tests/golden/*.json, written by tests/tools/make_golden.py from the oracle).
 CPU: the oracle still reproduces them bit-for-bit-ish (regression pin).  GPU: the CUDA step in the
 fp32 validation mode matches them to rel 1e-5 and in bf16 mode the loss terms to 2e-3."""
 import glob

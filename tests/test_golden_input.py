@@ -1,4 +1,4 @@
-"""Committed golden vectors of the input pipeline (tests/golden/input/*.json, written by tools/make_golden_input.py
+"""Committed golden vectors of the input pipeline (tests/golden/input/*.json, written by tests/tools/make_golden_input.py
 from oracle/input_oracle.py).  CPU: the oracle and the kernel's own source built for the host reproduce them bit
 for bit.  GPU: gmvae_binarize through the C ABI reproduces the 784-wide, rank-0 cases."""
 import ctypes as C

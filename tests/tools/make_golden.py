@@ -4,13 +4,13 @@ ORACLE against regressions and give the GPU tests a committed target; they are n
 outputs).  Inputs are regenerated from seeds; expectations are the loss terms, per-tensor gradient
 norms and a few sampled gradient entries in float64.
 
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 """
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
@@ -37,7 +37,7 @@ def main():
             idx = torch.randint(0, flat.numel(), (4,), generator=g).tolist()
             samples[n] = [[i, flat[i].item()] for i in idx]
         rec = {
-            "generator": "tools/make_golden.py (oracle/gmvae_oracle.py, float64)",
+            "generator": "tests/tools/make_golden.py (oracle/gmvae_oracle.py, float64)",
             "config": cfg, "params_seed": 2024, "data_seed": 1234, "noise_seed": 4321,
             "x_sum": int(x.sum()), "eps_sum": eps.double().sum().item(),
             "terms": {k: terms[k].item() for k in ("loss", "nll", "kl_div_z", "nent")},

@@ -3,7 +3,7 @@ Like the step's golden files these pin the ORACLE and give the CUDA kernel a com
 reference outputs (TF's stateful uniform generator cannot be reproduced).  Intensities are regenerated
 from a seed; the expectation is the binarised batch, bit-packed and hex-encoded.
 
-    python tools/make_golden_input.py
+    python tests/tools/make_golden_input.py
 """
 import hashlib
 import json
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import input_oracle as O  # noqa: E402
 
@@ -43,7 +43,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     for case in CASES:
         x = expected(case)
-        rec = dict(case, generator="tools/make_golden_input.py (oracle/input_oracle.py)",
+        rec = dict(case, generator="tests/tools/make_golden_input.py (oracle/input_oracle.py)",
                    intensity_sha256=hashlib.sha256(intensities(case).tobytes()).hexdigest(),
                    row_index=None if not case["gather"] else row_index(case).tolist(),
                    x_packbits_hex=np.packbits(x.reshape(-1)).tobytes().hex(), x_ones=int(x.sum()))
@@ -54,7 +54,7 @@ def main():
              for s, t, c in [(0, 0, 0), (2 ** 64 - 1, 2 ** 64 - 1, 2 ** 64 - 1), (0x299F31D0A4093822, 0x0370734413198A2E, 0x85A308D3243F6A88),
                              (1234, O.BINARIZE_STREAM, 0), (1234, O.BINARIZE_STREAM + 1, 2 ** 33 + 9)]]
     with open(os.path.join(out_dir, "philox_words.json"), "w") as f:
-        json.dump({"generator": "tools/make_golden_input.py", "note": "first three = Random123 kat_vectors (philox4x32, 10 rounds)",
+        json.dump({"generator": "tests/tools/make_golden_input.py", "note": "first three = Random123 kat_vectors (philox4x32, 10 rounds)",
                    "cases": words}, f, indent=1)
 
 
