@@ -42,6 +42,12 @@ def test_oracle_reproduces_golden(path):
         flat = grads[n].reshape(-1)
         for i, v in pts:
             assert abs(flat[i].item() - v) <= 1e-12 + 1e-9 * abs(v)
+    if "terms_marginal" in rec:                                       # objective M on the same inputs, eps [B, K, Z]
+        eps_m = torch.randn(cfg["batch"], spec.mixture_components, spec.latent_size,
+                            generator=torch.Generator().manual_seed(rec["noise_seed"]))
+        tm, _ = O.loss_and_grads(spec, params, x, eps_m, u, "marginal")
+        for k, v in rec["terms_marginal"].items():
+            assert abs(tm[k].item() - v) <= 1e-11 * max(1.0, abs(v)), ("marginal", k)
 
 
 @pytest.mark.gpu
