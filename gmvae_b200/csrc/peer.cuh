@@ -61,6 +61,16 @@ __host__ __device__ inline void push_target(const Layout& L, int rank, int64_t i
   owner = (int)(i4 / L.cap4);
   dst4 = (int64_t)rank * L.cap4 + (i4 - (int64_t)owner * L.cap4);
 }
+// data written by a peer: read through L2 (the point of coherence for peer writes), never from a stale L1 line
+struct LoadPeerWritten {
+  __host__ __device__ float4 operator()(const float4* p) const {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+  }
+};
 // phase B: sum of the `world` slots of element i of my shard, in rank order
 template <class Load>
 __host__ __device__ inline float4 reduce_slots(const Layout& L, const float4* recv, int64_t i, Load ld) {
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(Layout L, int rank, Pee
   const int64_t len4 = shard_len4(L, rank);
   const float4* recv = P.recv[rank];
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < len4; i += (int64_t)gridDim.x * THREADS) {
-    const float4 s = reduce_slots(L, recv, i, [](const float4* p) { return __ldcg(p); });
+    const float4 s = reduce_slots(L, recv, i, LoadPeerWritten());
     const int64_t d = red_index(L, rank, i);
     for (int p = 0; p < L.world; ++p) P.red[p][d] = s;
   }

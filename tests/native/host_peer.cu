@@ -31,7 +31,7 @@ extern "C" __attribute__((visibility("default"))) int host_peer_allreduce(int wo
   }
   for (int rank = 0; rank < world; ++rank)                          // phase B
     for (int64_t i = 0; i < shard_len4(L, rank); ++i) {
-      const float4 s = reduce_slots(L, P.recv[rank], i, [](const float4* p) { return *p; });
+      const float4 s = reduce_slots(L, P.recv[rank], i, LoadPeerWritten());
       for (int p = 0; p < world; ++p) P.red[p][red_index(L, rank, i)] = s;
     }
   for (int rank = 0; rank < world; ++rank) {                        // phase C
