@@ -25,7 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ["NCCL_DEBUG"] = os.environ.get("GMVAE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+# NCCL_DEBUG is left as the caller set it (the driver reads the communicator lines NCCL prints); GMVAE_NCCL_DEBUG overrides.
+if os.environ.get("GMVAE_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["GMVAE_NCCL_DEBUG"]
 
 import torch  # noqa: E402
 
@@ -261,6 +263,12 @@ def run_gpu_arm(args, w):
         for _ in range(3):
             step()                                # keep the GPU under load until the sampler ticks
         barrier()
+        # Device-side rendezvous: the ranks leave the host barrier a few hundred microseconds to milliseconds apart; two
+        # untimed steps (each ends in the gradient all-reduce, which no rank leaves before every rank has entered it) line
+        # the streams up, so the first timed event does not contain the start skew.
+        for _ in range(2 if world > 1 else 0):
+            flush_l2(l2_buf)
+            step()
         if rank == 0:
             sampler.mark()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -271,7 +279,9 @@ def run_gpu_arm(args, w):
             ev[i][1].record(side)
         barrier()
         clocks = sampler.stop() if rank == 0 else None
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+        dev_ms = sum(step_ms)
+        med_ms = step_ms[len(step_ms) // 2]
         loss_terms = eng.loss_buf.cpu().tolist()
 
         # ---- per-kernel-class device time: CUDA events after every launch of 3 eager steps --------
@@ -332,9 +342,9 @@ def run_gpu_arm(args, w):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, med_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t.tolist()
+        dev_ms, e2e_ms, med_ms = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,6 +359,8 @@ def run_gpu_arm(args, w):
         if tj and world == 1 and B == w["batch"]:
             traffic = tj["dram_bytes_tc_gemm_per_step"] / max(tj["tc_launches_per_step"], 1)
     fps = flops_per_sample(w, args.objective)
+    # `value` is the mean over EXACTLY args.steps timed steps (max over ranks); the median per-step time is reported beside it
+    # (a one-off stall -- clock ramp, a late rank -- moves the mean of a 20-step run, not the median)
     ms_per_step = dev_ms / args.steps
     value = world * B * args.steps / (dev_ms * 1e-3)
     step_tf = (B * fps) / (ms_per_step * 1e-3) / 1e12
@@ -358,7 +370,8 @@ def run_gpu_arm(args, w):
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     line = {
         "metric": "GMVAE train samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_median": med_ms,
+        "ms_per_step_max": step_ms[-1], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": w["desc"], "objective": args.objective, "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "L2 flushed (256 MB write) between timed steps", "graph": not args.no_graph,

@@ -63,6 +63,8 @@ SYMBOLS = {
     "gmvae_debug_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "gmvae_debug_noise": (_I, [_P, _P, _I64, _P, _I64, _P]),
     "gmvae_debug_chain_trace": (_I, [_P, _P, _I]),
+    "gmvae_debug_chain_jobstat": (_I, [_P, _P]),
+    "gmvae_debug_chain_jobs": (_I, [_P, C.POINTER(C.c_int), _I]),
     "gmvae_profile_enable": (_I, [_P, _I]),
     "gmvae_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _I]),
     "gmvae_launch_count": (_I64, [_P]),

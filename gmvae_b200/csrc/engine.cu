@@ -188,6 +188,8 @@ struct gmvae_handle {
   int chain_tiles = 0;
   int* chain_counters = nullptr; int chain_counter_cap = 0, chain_counter_next = 0;
   long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
+  unsigned long long* chain_jobstat = nullptr;     // test hook (gmvae_debug_chain_jobstat): 8 counters per job of the step's first chained launch
+  std::vector<int> chain_jobdesc;                  // 8 ints per job of that launch: kind, M, N, k-blocks, tiles, splits, block_n, ndeps
   bool chain_flush_after = false;
   bool row_jobs = false;                          // this step: distribution heads run as row jobs of the chained kernel
   // a y head to be fused into the epilogue of the next thin fp32 GEMM job (set by the step driver, consumed by chain_add)
@@ -417,12 +419,21 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain.counters = h->chain_counters;
   h->chain.trace = (h->chain_trace && h->chain_launch_idx < 8) ? h->chain_trace + (size_t)h->chain_launch_idx * 64 * 16 : nullptr;
   h->chain.trace_cta = h->chain_trace_cta;
+  h->chain.jobstat = (h->chain_jobstat && h->chain_launch_idx == 0) ? h->chain_jobstat : nullptr;
+  if (h->chain.jobstat) {
+    h->chain_jobdesc.clear();
+    for (int j = 0; j < h->chain.njobs; ++j) {
+      const tc::ChainJob& J = h->chain.jobs[j];
+      const int d[8] = {J.kind, J.M, J.N, J.kb1 + J.kb2, J.total_tiles, J.num_splits, J.block_n, J.ndeps};
+      h->chain_jobdesc.insert(h->chain_jobdesc.end(), d, d + 8);
+    }
+  }
   h->chain_launch_idx++;
   const int grid = std::min(h->chain_tiles, tc::num_sms());
   if (h->chain.njobs <= tc::CHAIN_SMALL_JOBS && h->chain.nmaps <= tc::CHAIN_SMALL_MAPS) {
     static tc::ChainParamsSmall small;                      // the launch copies it
     small.njobs = h->chain.njobs; small.nmaps = h->chain.nmaps; small.counters = h->chain.counters;
-    small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta;
+    small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta; small.jobstat = h->chain.jobstat;
     memcpy(small.maps, h->chain.maps, sizeof(CUtensorMap) * h->chain.nmaps);
     memcpy(small.jobs, h->chain.jobs, sizeof(tc::ChainJob) * h->chain.njobs);
     GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
@@ -524,6 +535,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   J.block_n = block_n; J.a_mn = a_mn ? 1 : 0; J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
   J.tiles_n = tiles_n; J.tiles_mn = tiles_m * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
   J.ndeps = ndeps; J.epi_dep = epi_dep;
+  J.rot = (tiles_n > 1 && N % block_n != 0 && !a_mn) ? 1 : 0;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
   const char *lo, *hi;
   writer_range(epi, M, lo, hi);
@@ -568,7 +580,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
 // `reads`: buffers whose rows it consumes; `writes`: {pointer, bytes} of every buffer it produces.
 template <class P>
 static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::initializer_list<const void*> reads,
-                          std::initializer_list<std::pair<const void*, size_t>> writes, cudaStream_t st) {
+                          std::initializer_list<std::pair<const void*, size_t>> writes, cudaStream_t st, int sub = 1) {
   static_assert(sizeof(P) <= tc::CHAIN_EPI_BYTES, "row-job parameters do not fit the job record");
   const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0;
@@ -591,7 +603,7 @@ static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::i
   tc::ChainJob& J = h->chain.jobs[h->chain.njobs];
   memset(&J, 0, sizeof(J));
   J.M = M; J.N = 0; J.kind = kind; J.num_splits = 1;
-  J.tiles_n = 1; J.tiles_mn = tiles_m; J.total_tiles = tiles_m; J.tile_base = h->chain_tiles;
+  J.tiles_n = sub; J.tiles_mn = tiles_m * sub; J.total_tiles = tiles_m * sub; J.tile_base = h->chain_tiles;   // sub tiles per 128-row block
   J.ndeps = ndeps; J.epi_dep = -1;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
   J.sig_base = -1;
@@ -863,9 +875,16 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       GM_LAUNCHED(h, st, PC_MISC);
       if (need_noise) {
         GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, uu, nu,
-                               (const DeviceState*)h->state, (uint64_t)h->rank));
+                               (const DeviceState*)h->state, (uint64_t)h->rank, 1));
         GM_LAUNCHED(h, st, PC_MISC);
       }
+    }
+    // The q(y|x) head consumes Gumbel noise g = -log(-log u): drawn that way above, converted here when u was injected.
+    if (gm && u) {
+      const int64_t nuu = (int64_t)B * K;
+      GM_CHECK_CUDA(launch_k(gumbel_from_u_kernel, dim3((unsigned)((nuu + 255) / 256)), dim3(256), 0, st, true, u, uu, nuu));
+      GM_LAUNCHED(h, st, PC_MISC);
+      u = uu;
     }
     if (!eps) eps = e;
     if (gm && !u) u = uu;
@@ -1024,7 +1043,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     const bool rows_ok = h->chain_on && h->row_jobs && v4 && prior_mode != 1 && z_f32 == nullptr;
     if (rows_ok) {
       tc::RowsZFwd prm{enc_out, eps, prior_out, prior_mode, Z, c.raw_sigma_bias, c.sigma_min, inv_bg, reinterpret_cast<bf16*>(z_act), Zp, acc};
-      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_FWD, prm, B, {enc_out, eps, prior_out}, {{z_act, (size_t)B * Zp * 2}}, st));
+      GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_FWD, prm, B, {enc_out, eps, prior_out}, {{z_act, (size_t)B * Zp * 2}}, st, 4));
     } else {
     GM_TRY(chain_flush(h, st));
     if (v4) {
@@ -1092,7 +1111,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
                        reinterpret_cast<bf16*>(d_prior_out), Z2p, h->grads + enc_last.b_off,
                        gm ? h->grads + h->prior_gmm.layers[0].b_off : (float*)nullptr};
       GM_TRY(chain_add_rows(h, tc::EK_ROWS_Z_BWD, prm, B, {dz, enc_out, prior_out, eps},
-                            {{d_enc_out, (size_t)B * Z2p * 2}, {gm ? d_prior_out : nullptr, (size_t)B * Z2p * 2}}, st));
+                            {{d_enc_out, (size_t)B * Z2p * 2}, {gm ? d_prior_out : nullptr, (size_t)B * Z2p * 2}}, st, 4));
     } else {
     GM_TRY(chain_flush(h, st));
     const bool v4 = std::is_same<A, bf16>::value && enc_bias_fused && Z % 4 == 0 && aligned16(eps) && aligned16(enc_out) && aligned16(dz) &&
@@ -1228,7 +1247,7 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
     float* e = h->buf<float>("eps");
     const int64_t ne = (int64_t)B * K * Z, q = (ne + 3) / 4;
     GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, (float*)nullptr, (int64_t)0,
-                           (const DeviceState*)h->state, (uint64_t)h->rank));
+                           (const DeviceState*)h->state, (uint64_t)h->rank, 0));
     GM_LAUNCHED(h, st, PC_MISC);
     eps = e;
   }
@@ -1757,7 +1776,7 @@ int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int6
   int64_t q = (n_eps + 3) / 4 + (n_u + 3) / 4;
   if (q == 0) return 0;
   GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, eps, n_eps, u, n_u,
-                         (const DeviceState*)h->state, (uint64_t)h->rank));
+                         (const DeviceState*)h->state, (uint64_t)h->rank, 0));
   return 0;
 }
 
@@ -1797,6 +1816,21 @@ int gmvae_debug_chain_trace(gmvae_handle* h, long long* trace, int cta) {
   GM_REQUIRE(h, "null handle");
   h->chain_trace = trace; h->chain_trace_cta = cta;
   return 0;
+}
+
+// Test hook: per-job counters (8 x uint64 per job, gemm_chain.cuh ChainParamsT::jobstat) of the first chained launch of the
+// following steps; `stat` = device buffer of 8 * 40 uint64 pre-set by the caller ([0] of every job to ~0, the rest 0).
+int gmvae_debug_chain_jobstat(gmvae_handle* h, unsigned long long* stat) {
+  GM_REQUIRE(h, "null handle");
+  h->chain_jobstat = stat;
+  return 0;
+}
+// Descriptions of the jobs of that launch: 8 ints per job (kind, M, N, k-blocks, tiles, splits, block_n, ndeps); returns the job count.
+int gmvae_debug_chain_jobs(gmvae_handle* h, int* out, int cap_jobs) {
+  GM_REQUIRE(h && out, "null argument");
+  const int n = std::min(cap_jobs, (int)h->chain_jobdesc.size() / 8);
+  for (int i = 0; i < 8 * n; ++i) out[i] = h->chain_jobdesc[i];
+  return n;
 }
 
 int gmvae_profile_enable(gmvae_handle* h, int on) {

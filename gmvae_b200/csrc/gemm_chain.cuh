@@ -76,6 +76,7 @@ struct alignas(16) ChainJob {
   int epi_dep;                       // index into deps of the job that wrote the epilogue's own operand (ReLU mask source), or -1
   ChainDep deps[CHAIN_MAX_DEPS];
   alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
+  int rot;                           // 1: the n-tile index is rotated by the row block (see chain_tile)
   int fuse;                          // EK_STORE_F32 jobs with N <= 16: a y head applied to the row in the epilogue (EK_ROWS_Y_FWD / _BWD), 0 = none
   alignas(16) unsigned char epi2[CHAIN_EPI2_BYTES];   // its parameters (RowsYFwd / RowsYBwd)
 };
@@ -88,6 +89,9 @@ struct ChainParamsT {
   int* counters;
   long long* trace;    // test hook: clock64 stamps of CTA `trace_cta`, 16 per processed tile (null in production)
   int trace_cta;
+  unsigned long long* jobstat;   // test hook: 8 counters per job over ALL CTAs (globaltimer ns): [0] first tile start, [1] last tile end,
+                                 // [2] producer dependency wait, [3] MMA issue->commit, [4] epilogue rows, [5] epilogue wait for the
+                                 // accumulator, [6] tiles, [7] MMA wait for a free accumulator (null in production)
   alignas(64) CUtensorMap maps[MAXM];
   ChainJob jobs[MAXJ];
 };
@@ -102,6 +106,11 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 // bounded like mbar_wait: a scheduling bug ends as a trapped launch, not as a hung GPU
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
   if (ld_acquire_gpu(p) >= target) return;
@@ -116,6 +125,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int mn
   const uint64_t lbo = mn_major ? (uint64_t)(BLOCK_K * 128) : 0;
   const uint64_t sbo = 1024;
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Tile l of a job -> (k-split z, row block mb, first column n0).  n fastest, then m, then k-split.  With J.rot the n-tile index
+// is rotated by the row block: a job whose last n-tile is ragged (784 = 3 x 256 + 16) has cheap and expensive tiles, and since
+// the CTAs walk the tile sequence with a stride (148) that is a multiple of tiles_n, every CTA would otherwise see one n-tile
+// index only -- a quarter of the CTAs all the cheap tiles, the rest all the expensive ones.
+__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int& z, int& mb, int& n0) {
+  z = l / J.tiles_mn;
+  const int mn = l - z * J.tiles_mn;
+  mb = mn / J.tiles_n;
+  int nt = mn - mb * J.tiles_n;
+  if (J.rot) { nt += mb % J.tiles_n; if (nt >= J.tiles_n) nt -= J.tiles_n; }
+  n0 = nt * J.block_n;
 }
 
 struct ChainShared {
@@ -173,37 +195,77 @@ __device__ __forceinline__ void pack16(const float* v, uint4& lo, uint4& hi) {
 // Warp-collective (all 32 lanes call; `valid` masks rows beyond the batch) and deliberately NOT inlined: the thin
 // GEMM jobs that host them sit on the critical path of the chain and must not inherit their register footprint.
 // forward: lg = logits (with bias).  Writes y (fp32 + zero-padded bf16 operand row), returns sum_k p log p of the row.
+// Math of the heads inside the chained kernel (bf16 training step only): fast intrinsics.  exp / log arguments are logits
+// and softmax sums of magnitude O(1-100): __expf / __logf are good to ~2 ulp there (abs error of log(1+e), 1+e in (1,2]:
+// ~1e-7), far inside the bf16 storage the results go to.  The fp32 validation mode never runs these (kernels.cuh heads).
+__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_softplus(float t) { return fmaxf(t, 0.f) + __logf(1.f + __expf(-fabsf(t))); }
+__device__ __forceinline__ float fast_sigmoid(float t) {
+  const float e = __expf(-fabsf(t));
+  const float s = __fdividef(1.f, 1.f + e);
+  return t >= 0.f ? s : e * s;
+}
+// row of K floats at p (8-byte aligned when K is even): vector loads / stores
+__device__ __forceinline__ void ld_row16(const float* p, int K, float* v, float fill) {
+  if ((K & 1) == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      if (k < K) { const float2 t = __ldcg(reinterpret_cast<const float2*>(p + k)); v[k] = t.x; v[k + 1] = t.y; }
+      else { v[k] = fill; v[k + 1] = fill; }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = k < K ? __ldcg(p + k) : fill;
+  }
+}
+__device__ __forceinline__ void st_row16(float* p, int K, const float* v) {
+  if ((K & 1) == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2)
+      if (k < K) *reinterpret_cast<float2*>(p + k) = make_float2(v[k], v[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < K) p[k] = v[k];
+  }
+}
 __device__ __noinline__ float y_head_fwd_row(const float* lg, const RowsYFwd& prm, int64_t row, bool valid) {
   if (!valid) return 0.f;
   const int K = prm.K;
   float a[16];
+  ld_row16(prm.u + row * K, K, a, 0.f);                       // Gumbel noise g = -log(-log u), prepared by the step's first kernel
   float ml = -INFINITY, ma = -INFINITY;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    a[k] = -INFINITY;
     if (k < K) {
-      a[k] = (lg[k] - logf(-logf(__ldcg(prm.u + row * K + k)))) * prm.inv_T;
+      a[k] = (lg[k] + a[k]) * prm.inv_T;
       ml = fmaxf(ml, lg[k]);
+    } else {
+      a[k] = -INFINITY;
     }
     ma = fmaxf(ma, a[k]);
   }
   float sl = 0.f, sa = 0.f;
+  float pl[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-    if (k < K) { a[k] = expf(a[k] - ma); sl += expf(lg[k] - ml); sa += a[k]; }
-  const float lse = ml + logf(sl), inv_sa = 1.f / sa;
+  for (int k = 0; k < 16; ++k) {
+    pl[k] = 0.f;
+    if (k < K) { a[k] = __expf(a[k] - ma); pl[k] = __expf(lg[k] - ml); sl += pl[k]; sa += a[k]; }
+  }
+  const float lse = ml + __logf(sl), inv_sa = __fdividef(1.f, sa), inv_sl = __fdividef(1.f, sl);
   float y[16];
   float ent = 0.f;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     y[k] = 0.f;
     if (k < K) {
-      const float logp = lg[k] - lse;
-      ent += expf(logp) * logp;
+      ent = fmaf(pl[k] * inv_sl, lg[k] - lse, ent);          // p log p
       y[k] = a[k] * inv_sa;
-      prm.y_f32[row * K + k] = y[k];
     }
   }
+  st_row16(prm.y_f32 + row * K, K, y);
   uint4* dst = reinterpret_cast<uint4*>(prm.y_act + row * prm.ld_yact);
   dst[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
   if (prm.ld_yact > 8) dst[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
@@ -218,37 +280,37 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
   for (int k = 0; k < 16; ++k) o[k] = 0.f;
   if (valid) {
     float y[16];
+    ld_row16(prm.logits + row * K, K, lg, -INFINITY);
+    ld_row16(prm.y_f32 + row * K, K, y, 0.f);
     float ml = -INFINITY, ydy = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      lg[k] = -INFINITY; y[k] = 0.f;
-      if (k < K) {
-        lg[k] = __ldcg(prm.logits + row * K + k);
-        y[k] = __ldcg(prm.y_f32 + row * K + k);
-        ml = fmaxf(ml, lg[k]);
-        ydy += y[k] * g[k];
-      }
-    }
-    float sl = 0.f;
-#pragma unroll
     for (int k = 0; k < 16; ++k)
-      if (k < K) sl += expf(lg[k] - ml);
-    const float lse = ml + logf(sl);
+      if (k < K) { ml = fmaxf(ml, lg[k]); ydy = fmaf(y[k], g[k], ydy); }
+    float sl = 0.f;
+    float pl[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      pl[k] = 0.f;
+      if (k < K) { pl[k] = __expf(lg[k] - ml); sl += pl[k]; }
+    }
+    const float lse = ml + __logf(sl), inv_sl = __fdividef(1.f, sl);
     float plogp = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k)
-      if (k < K) { lg[k] -= lse; plogp += expf(lg[k]) * lg[k]; }
+      if (k < K) { lg[k] -= lse; pl[k] *= inv_sl; plogp = fmaf(pl[k], lg[k], plogp); }
 #pragma unroll
     for (int k = 0; k < 16; ++k)
-      if (k < K) o[k] = __bfloat162float(__float2bfloat16_rn(y[k] * (g[k] - ydy) * prm.inv_T + expf(lg[k]) * (lg[k] - plogp) * prm.inv_bg));
+      if (k < K) o[k] = __bfloat162float(__float2bfloat16_rn(y[k] * (g[k] - ydy) * prm.inv_T + pl[k] * (lg[k] - plogp) * prm.inv_bg));
     uint4* dst = reinterpret_cast<uint4*>(prm.dlogits + row * prm.ld_out);
     dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     if (prm.ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const float t = warp_sum(o[k]);
-    if ((threadIdx.x & 31) == 0 && k < K && t != 0.f) atomicAdd(scs + k, t);
+    if (k < K) {                                              // warp-uniform
+      const float t = warp_sum(o[k]);
+      if ((threadIdx.x & 31) == 0 && t != 0.f) atomicAdd(scs + k, t);
+    }
   }
 }
 
@@ -265,7 +327,8 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
 // source of the backward pass arrives the same way (TMA load of the box into the patch).
 template <class Epi, int KIND>
 __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUtensorMap* maps, int* counters, const ChainShared& S, int& it,
-                                                   uint32_t& op_phase, int warp, int lane, long long* trace, int jidx) {
+                                                   uint32_t& op_phase, int warp, int lane, long long* trace, int jidx,
+                                                   unsigned long long* jobstat = nullptr) {
   constexpr int CW = 16;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
   const int G = gridDim.x;
@@ -294,9 +357,9 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     }
   };
   for (int l = first; l < J.total_tiles; l += G, ++it) {
-    const int z = l / tiles_mn, mn = l - z * tiles_mn;
-    const int mb = mn / tiles_n;
-    const int m0 = mb * BLOCK_M, n0 = (mn - mb * tiles_n) * BN;
+    int z, mb, n0;
+    chain_tile(J, l, z, mb, n0);
+    const int m0 = mb * BLOCK_M;
     const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
     const int mrow0 = m0 + quad * 32;
     const int m = mrow0 + lane;
@@ -305,7 +368,9 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     {
       const uint32_t sb = smem_addr(sbias);
-      for (int i = et; i < BN; i += EPI_WARPS * 32) sts32f(sb + 4 * i, (bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f);
+      float shift = 0.f;
+      if constexpr (KIND == EK_BCE) shift = epi.gen_bias;     // logits = MLP(z) + bias_init (base.py:135)
+      for (int i = et; i < BN; i += EPI_WARPS * 32) sts32f(sb + 4 * i, ((bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f) + shift);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     if (cs_dst && cs_n0 != n0) {
@@ -318,6 +383,8 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     const bool mvalid = m < M;
     const bool tr = trace && e == 0 && lane == 0 && it < 64;
     if (tr) { trace[16 * it + 6] = clock64(); trace[16 * it + 15] = jidx; trace[16 * it + 14] = l; }
+    const bool js = jobstat && e == 0 && lane == 0;
+    unsigned long long js_t0 = 0, js_t1 = 0;
     // The epilogue's own operand (ReLU mask source) is fetched ahead of the accumulator, i.e. possibly
     // before the TMA producer has seen this tile's dependencies: the warp checks the operand's producer itself.
     if (J.epi_dep >= 0) {
@@ -329,9 +396,11 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     auto wait_acc = [&]() {
       if (!acc_ready) {
         if (tr) trace[16 * it + 7] = clock64();
+        if (js) js_t0 = gtimer();
         mbar_wait(&S.tmem_full_bar[as], ap);
         tc_fence_after();
         if (tr) trace[16 * it + 8] = clock64();
+        if (js) js_t1 = gtimer();
         acc_ready = true;
       }
     };
@@ -360,9 +429,12 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
             for (int i = 0; i < CW; ++i) lg[i] = fmaf(v[i], epi.scale, sbias[i]);
             if (J.fuse == EK_ROWS_Y_FWD) {
               if (mvalid) {
+                if (epi.ld == N) st_row16(epi.out + (int64_t)m * epi.ld, N, lg);   // logits: read again by the backward head
+                else {
 #pragma unroll
-                for (int i = 0; i < CW; ++i)
-                  if (i < N) epi.out[(int64_t)m * epi.ld + i] = lg[i];            // logits: read again by the backward head
+                  for (int i = 0; i < CW; ++i)
+                    if (i < N) epi.out[(int64_t)m * epi.ld + i] = lg[i];
+                }
               }
               fuse_acc += y_head_fwd_row(lg, *reinterpret_cast<const RowsYFwd*>(J.epi2), (int64_t)m, mvalid);
             } else {
@@ -480,22 +552,42 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
                 }
                }
               } else if constexpr (KIND == EK_BCE) {
-                const uint8_t* xb = reinterpret_cast<const uint8_t*>(&xq[c]);
                 const int nvalid = min(CW, N - (n0 + ci * CW));
                 float ll = 0.f;
+                if (nvalid == CW && m0 + BLOCK_M <= M) {
+                  // Whole chunk inside the matrix (warp-uniform).  x in {0,1}: with t = (1 - 2x) l, i.e. l with its sign bit
+                  // flipped where x = 1,   x l - softplus(l) = -softplus(t)   and   sigmoid(l) - x = (1 - 2x) sigmoid(t):
+                  // one exponential, one reciprocal, one logarithm and ~14 other instructions per element (the epilogue warps
+                  // are issue-bound here: 25 K elements per tile against an 8-k-block main loop).
+                  const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xq[c]);
 #pragma unroll
-                for (int i = 0; i < CW; ++i) {
-                  const float lg = v[i] + epi.gen_bias + bb[i];
-                  // byte -> float without the conversion pipe: 2^23 + b is exact in fp32
-                  const float xv = __uint_as_float(0x4B000000u | (uint32_t)xb[i]) - 8388608.f;
-                  // bf16 mode only: fast intrinsics (exp(-|l|) in (0,1], log(1+e) with 1+e in (1,2]: abs error ~1e-7)
-                  const float ex = __expf(-fabsf(lg));
-                  const float sp = fmaxf(lg, 0.f) + __logf(1.f + ex);
-                  const float inv1pe = __fdividef(1.f, 1.f + ex);
-                  const float sg = lg >= 0.f ? inv1pe : ex * inv1pe;
-                  const bool ok = mvalid && i < nvalid;
-                  ll += ok ? fmaf(xv, lg, -sp) : 0.f;
-                  v[i] = ok ? (sg - xv) * epi.inv_bg : 0.f;
+                  for (int i = 0; i < CW; ++i) {
+                    const uint32_t sgn = (xw[i >> 2] << (31 - 8 * (i & 3))) & 0x80000000u;     // bit 0 of byte i -> sign bit
+                    const float t = __uint_as_float(__float_as_uint(v[i] + bb[i]) ^ sgn);
+                    const float e = exp2f_approx(fabsf(t) * -1.4426950408889634f);
+                    const float d = 1.f + e;
+                    const float r = rcp_approx(d);
+                    ll -= fmaxf(t, 0.f);
+                    ll = fmaf(lg2_approx(d), -0.6931471805599453f, ll);
+                    const float sg = r * (t >= 0.f ? 1.f : e);
+                    v[i] = __uint_as_float(__float_as_uint(sg * epi.inv_bg) ^ sgn);
+                  }
+                } else {
+                  const uint8_t* xb = reinterpret_cast<const uint8_t*>(&xq[c]);
+#pragma unroll
+                  for (int i = 0; i < CW; ++i) {
+                    const float lg = v[i] + bb[i];
+                    // byte -> float without the conversion pipe: 2^23 + b is exact in fp32
+                    const float xv = __uint_as_float(0x4B000000u | (uint32_t)xb[i]) - 8388608.f;
+                    // bf16 mode only: fast intrinsics (exp(-|l|) in (0,1], log(1+e) with 1+e in (1,2]: abs error ~1e-7)
+                    const float ex = __expf(-fabsf(lg));
+                    const float sp = fmaxf(lg, 0.f) + __logf(1.f + ex);
+                    const float inv1pe = __fdividef(1.f, 1.f + ex);
+                    const float sg = lg >= 0.f ? inv1pe : ex * inv1pe;
+                    const bool ok = mvalid && i < nvalid;
+                    ll += ok ? fmaf(xv, lg, -sp) : 0.f;
+                    v[i] = ok ? (sg - xv) * epi.inv_bg : 0.f;
+                  }
                 }
                 epi.partial += ll;
               }
@@ -542,6 +634,13 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
       }
     }
     if (tr) trace[16 * it + 10] = clock64();
+    if (js) {
+      const unsigned long long t2 = gtimer();
+      atomicMax(jobstat + 8 * jidx + 1, t2);
+      atomicAdd(jobstat + 8 * jidx + 4, t2 - js_t1);
+      atomicAdd(jobstat + 8 * jidx + 5, js_t1 - js_t0);
+      atomicAdd(jobstat + 8 * jidx + 6, 1ull);
+    }
   }
   epi.finish_warp();
   if constexpr (KIND == EK_STORE_F32) {
@@ -568,7 +667,8 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 template <int KIND, class P>
-__device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters, const ChainShared& S, int warp, int lane) {
+__device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters, const ChainShared& S, int warp, int lane,
+                                               unsigned long long* jobstat = nullptr, int jidx = 0) {
   const P prm = *reinterpret_cast<const P*>(J.epi);
   const int G = gridDim.x;
   const int first = (((int)blockIdx.x - J.tile_base) % G + G) % G;
@@ -585,13 +685,20 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
     for (int i = et; i < 256; i += NT) S.scs_all[i] = 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
   }
+  // A tile is 1/sub of a 128-row block (J.tiles_n = sub): the z heads use 32-row tiles -- one float4 item per epilogue thread -- so
+  // that a head stage spreads over every CTA instead of one CTA per row block; every tile signals its block's counter.
+  const int sub = J.tiles_n, rpt = BLOCK_M / sub;
   for (int l = first; l < J.total_tiles; l += G) {
-    const int mb = l, m0 = mb * BLOCK_M;
-    const int rows = min(BLOCK_M, M - m0);
+    const int mb = l / sub, m0 = l * rpt;
+    const int rows = max(0, min(rpt, M - m0));
+    const bool js = jobstat && warp == 2 && lane == 0;
+    unsigned long long js_t0 = 0, js_t1 = 0;
+    if (js) js_t0 = gtimer();
     if (lane == 0) {
       for (int d = 0; d < J.ndeps; ++d) wait_counter(counters + J.deps[d].base + mb, J.deps[d].target);
     }
     __syncwarp();
+    if (js) { js_t1 = gtimer(); atomicMin(jobstat + 8 * jidx + 0, js_t0); atomicAdd(jobstat + 8 * jidx + 2, js_t1 - js_t0); }
     if constexpr (KIND == EK_ROWS_Z_FWD) {
       const int Z = prm.Z, tpr = Z >> 2;
       for (int t = et; t < rows * tpr; t += NT) {
@@ -604,18 +711,21 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
         float z[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float sg = fmaxf(softplus_f(RAW[q] + prm.c), prm.sigma_min);
+          const float sg = fmaxf(fast_softplus(RAW[q] + prm.c), prm.sigma_min);
           z[q] = fmaf(sg, E[q], MU[q]);
-          const float logq = -0.5f * E[q] * E[q] - logf(sg);
-          float logp = 0.f;
+          // log q - log p = -e^2/2 - log sg + tt^2/2 + log sp = (tt^2 - e^2)/2 + log(sp / sg)
+          float d = -0.5f * E[q] * E[q];
           if (prm.prior_mode == 0) {
-            logp = -0.5f * z[q] * z[q];
+            d = fmaf(0.5f * z[q], z[q], d) - __logf(sg);
           } else if (prm.prior_mode == 2) {
-            const float sp = fmaxf(softplus_f(RP[q] + prm.c), prm.sigma_min);
-            const float tt = (z[q] - MP[q]) / sp;
-            logp = -0.5f * tt * tt - logf(sp);
+            const float sp = fmaxf(fast_softplus(RP[q] + prm.c), prm.sigma_min);
+            const float isp = __fdividef(1.f, sp);
+            const float tt = (z[q] - MP[q]) * isp;
+            d = fmaf(0.5f * tt, tt, d) - __logf(sg * isp);
+          } else {
+            d -= __logf(sg);
           }
-          red_acc += logq - logp;
+          red_acc += d;
         }
         *reinterpret_cast<uint2*>(prm.z_act + (int64_t)b * prm.ld_z + j) = make_uint2(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]));
       }
@@ -633,7 +743,11 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
         float g0[4], g1[4], a0[4], a1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float spq = softplus_f(RAW[q] + prm.c);
+          // softplus(t) and sigmoid(t) from ONE exponential: e = exp(-|t|), softplus = max(t,0) + log(1+e), sigmoid = (t>=0 ? 1 : e)/(1+e)
+          const float tq = RAW[q] + prm.c;
+          const float eq = __expf(-fabsf(tq)), iq = __fdividef(1.f, 1.f + eq);
+          const float spq = fmaxf(tq, 0.f) + __logf(1.f + eq);
+          const float sgm_q = tq >= 0.f ? iq : eq * iq;
           const float sg = fmaxf(spq, prm.sigma_min);
           const float z = fmaf(sg, E[q], MU[q]);
           float dz = DZ[q];
@@ -641,18 +755,22 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
           if (prm.prior_mode == 0) {
             dz += z * prm.inv_bg;
           } else {
-            const float spp = softplus_f(RP[q] + prm.c);
+            const float tp = RP[q] + prm.c;
+            const float ep = __expf(-fabsf(tp)), ip = __fdividef(1.f, 1.f + ep);
+            const float spp = fmaxf(tp, 0.f) + __logf(1.f + ep);
+            const float sgm_p = tp >= 0.f ? ip : ep * ip;
             const float sp = fmaxf(spp, prm.sigma_min);
             const float d = z - MP[q];
-            const float isp2 = 1.f / (sp * sp);
+            const float isp = __fdividef(1.f, sp);
+            const float isp2 = isp * isp;
             dz += d * isp2 * prm.inv_bg;
-            const float dsp = (1.f / sp - d * d * isp2 / sp) * prm.inv_bg;
+            const float dsp = (isp - d * d * isp2 * isp) * prm.inv_bg;
             a0[q] = __bfloat162float(__float2bfloat16_rn(-d * isp2 * prm.inv_bg));
-            a1[q] = __bfloat162float(__float2bfloat16_rn(spp >= prm.sigma_min ? dsp * sigmoid_f(RP[q] + prm.c) : 0.f));
+            a1[q] = __bfloat162float(__float2bfloat16_rn(spp >= prm.sigma_min ? dsp * sgm_p : 0.f));
           }
-          const float dsg = dz * E[q] - prm.inv_bg / sg;
+          const float dsg = dz * E[q] - prm.inv_bg * __fdividef(1.f, sg);
           g0[q] = __bfloat162float(__float2bfloat16_rn(dz));
-          g1[q] = __bfloat162float(__float2bfloat16_rn(spq >= prm.sigma_min ? dsg * sigmoid_f(RAW[q] + prm.c) : 0.f));
+          g1[q] = __bfloat162float(__float2bfloat16_rn(spq >= prm.sigma_min ? dsg * sgm_q : 0.f));
           cs[q] += g0[q]; cs[4 + q] += g1[q]; cs[8 + q] += a0[q]; cs[12 + q] += a1[q];     // sums of the values as stored
         }
         *reinterpret_cast<uint2*>(prm.d_enc_out + (int64_t)b * prm.ld_out + j) = make_uint2(pack_bf16x2(g0[0], g0[1]), pack_bf16x2(g0[2], g0[3]));
@@ -668,7 +786,8 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
         const bool valid = et < rows;
         float lg[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) lg[k] = (valid && k < prm.K) ? __ldcg(prm.logits + row * prm.K + k) : -INFINITY;
+        for (int k = 0; k < 16; ++k) lg[k] = -INFINITY;
+        if (valid) ld_row16(prm.logits + row * prm.K, prm.K, lg, -INFINITY);
         red_acc += y_head_fwd_row(lg, prm, row, valid);
       }
     } else if constexpr (KIND == EK_ROWS_Y_BWD) {
@@ -687,6 +806,10 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
     if (lane == 0 && J.sig_base >= 0) {
       __threadfence();
       atomicAdd(counters + J.sig_base + mb, 1);
+    }
+    if (js) {
+      const unsigned long long t2 = gtimer();
+      atomicMax(jobstat + 8 * jidx + 1, t2); atomicAdd(jobstat + 8 * jidx + 4, t2 - js_t1); atomicAdd(jobstat + 8 * jidx + 6, 1ull);
     }
   }
   // ---- per-job reductions of this CTA
@@ -770,12 +893,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         const uint32_t tx_bytes = (uint32_t)(A_STAGE_BYTES + BN * BLOCK_K * 2);
         const int first = ((c - J.tile_base) % G + G) % G;
         for (int l = first; l < J.total_tiles; l += G, ++pit) {
-          const int z = l / tiles_mn, mn = l - z * tiles_mn;
-          const int mb = mn / tiles_n;
-          const int m0 = mb * BLOCK_M, n0 = (mn - mb * tiles_n) * BN;
+          int z, mb, n0;
+          chain_tile(J, l, z, mb, n0);
+          const int m0 = mb * BLOCK_M;
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
           const bool tr = trace && pit < 64;
           if (tr) trace[16 * pit + 0] = clock64();
+          unsigned long long js_t0 = 0;
+          if (p.jobstat) js_t0 = gtimer();
           if (J.ndeps > 0) {
             for (int d = 0; d < J.ndeps; ++d) {
               const ChainDep& D = J.deps[d];
@@ -790,6 +915,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
             fence_proxy_async_global();
           }
           if (tr) trace[16 * pit + 1] = clock64();
+          if (p.jobstat) { atomicMin(p.jobstat + 8 * j + 0, js_t0); atomicAdd(p.jobstat + 8 * j + 2, gtimer() - js_t0); }
           for (int kb = kb_begin; kb < kb_end; ++kb) {
             if (kb == kb1 && J.ndeps > 0) {
               // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
@@ -839,17 +965,20 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         const uint64_t b_step = b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         const int first = ((c - J.tile_base) % G + G) % G;
         for (int l = first; l < J.total_tiles; l += G, ++it) {
-          const int z = l / tiles_mn;
+          int z, mb_unused, n0;
+          chain_tile(J, l, z, mb_unused, n0);
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
           const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
           // a ragged last n-tile runs a narrower MMA (N multiple of 16): the zero-filled columns are not multiplied
-          const int n0 = ((l - z * tiles_mn) % J.tiles_n) * J.block_n;
           const int n_eff = min(J.block_n, (J.N - n0 + 15) & ~15);
           const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
           const bool tr = trace && it < 64;
           if (tr) trace[16 * it + 3] = clock64();
+          unsigned long long js_t0 = 0, js_t1 = 0;
+          if (p.jobstat) js_t0 = gtimer();
           mbar_wait(&tmem_empty_bar[as], ap ^ 1);
           tc_fence_after();
+          if (p.jobstat) js_t1 = gtimer();
           const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
           for (int kb = kb_begin; kb < kb_end; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -867,6 +996,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
           }
           umma_commit(&tmem_full_bar[as]);
           if (tr) trace[16 * it + 5] = clock64();
+          if (p.jobstat) { atomicAdd(p.jobstat + 8 * j + 3, gtimer() - js_t1); atomicAdd(p.jobstat + 8 * j + 7, js_t1 - js_t0); }
         }
       }
     }
@@ -878,16 +1008,16 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
 #ifndef GMVAE_NO_ROWS
-        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane); break;
-        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane); break;
-        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd>(J, p.counters, S, warp, lane); break;
-        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd>(J, p.counters, S, warp, lane); break;
+        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
 #endif
         default: break;
       }

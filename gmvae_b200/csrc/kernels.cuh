@@ -63,8 +63,12 @@ __global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restri
 // ---- noise (only when the caller does not inject it) -----------------------------------------
 // eps ~ N(0,1) (tf.random_normal inside MultivariateNormalDiag.sample), u ~ U(tiny,1)
 // (RelaxedOneHotCategorical.sample).  Keyed by (seed, step, stream id, element index).
+// `gumbel` != 0: the uniforms are stored as Gumbel noise g = -log(-log u) (what RelaxedOneHotCategorical.sample adds to the
+// logits) -- the two logarithms run here, in a fully parallel coalesced kernel, instead of in the
+// q(y|x) head, which sits on the critical path of the step.
+__device__ __forceinline__ float gumbel_of(float u) { return -logf(-logf(u)); }
 __device__ __forceinline__ void fill_noise_body(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
-                                                const DeviceState* st, uint64_t rank_stream, int64_t block) {
+                                                const DeviceState* st, uint64_t rank_stream, int64_t block, int gumbel = 0) {
   const uint64_t seed = st->seed, step = (uint64_t)st->step;
   int64_t i = block * blockDim.x + threadIdx.x;
   int64_t q_eps = (n_eps + 3) / 4, q_u = (n_u + 3) / 4;
@@ -82,14 +86,21 @@ __device__ __forceinline__ void fill_noise_body(float* __restrict__ eps, int64_t
     int64_t k = i - q_eps;
     Philox::gen(seed ^ (step * 0x9E3779B97F4A7C15ull), rank_stream * 2 + 1, (uint64_t)k, r);
     for (int j = 0; j < 4; ++j)
-      if (k * 4 + j < n_u) u[k * 4 + j] = u01(r[j]);
+      if (k * 4 + j < n_u) u[k * 4 + j] = gumbel ? gumbel_of(u01(r[j])) : u01(r[j]);
   }
 }
 __global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
-                                  const DeviceState* st, uint64_t rank_stream) {
+                                  const DeviceState* st, uint64_t rank_stream, int gumbel) {
   griddep_wait();
   griddep_launch();
-  fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, blockIdx.x);
+  fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, blockIdx.x, gumbel);
+}
+// injected uniforms (parity tests, run_model(..., gumbel_u=)) -> Gumbel noise
+__global__ void gumbel_from_u_kernel(const float* __restrict__ u, float* __restrict__ g, int64_t n) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] = gumbel_of(u[i]);
 }
 // first launch of a training step: blocks [0, x_blocks) convert the image bytes, the rest draw the noise
 template <typename T>
@@ -98,7 +109,7 @@ __global__ void prologue_kernel(const uint8_t* __restrict__ x, T* __restrict__ o
   griddep_wait();
   griddep_launch();
   if ((int)blockIdx.x < x_blocks) convert_x_body<T>(x, out, n, blockIdx.x);
-  else fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, (int64_t)blockIdx.x - x_blocks);
+  else fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, (int64_t)blockIdx.x - x_blocks, 1);
 }
 
 // ---- q(y|x) head, forward (gmvae.py:238-240, 262-263; utils.py:165-170) ------------------------
@@ -107,7 +118,7 @@ __global__ void prologue_kernel(const uint8_t* __restrict__ x, T* __restrict__ o
 // operand of encoder_gmm layer 0 / prior_gmm.
 constexpr int HEAD_MAXK = 128;
 template <typename ActT>
-__global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ u, int B, int K, float inv_T,
+__global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ gum, int B, int K, float inv_T,
                                   float inv_bg, float* __restrict__ y_f32, ActT* __restrict__ y_act, int ld_yact,
                                   float* __restrict__ acc) {
   griddep_wait();
@@ -125,8 +136,8 @@ __global__ void head_y_fwd_kernel(const float* __restrict__ logits, const float*
       l[i] = -INFINITY; a[i] = -INFINITY;
       if (k < K) {
         l[i] = logits[(int64_t)row * K + k];
-        // objective M passes u == null: y := softmax(logits) = q(y|x) itself
-        a[i] = u ? (l[i] - logf(-logf(u[(int64_t)row * K + k]))) * inv_T : l[i];
+        // gum = Gumbel noise -log(-log u); objective M passes null: y := softmax(logits) = q(y|x) itself
+        a[i] = gum ? (l[i] + gum[(int64_t)row * K + k]) * inv_T : l[i];
       }
       ml = fmaxf(ml, l[i]); ma = fmaxf(ma, a[i]);
     }
@@ -497,7 +508,7 @@ __global__ void head_z_bwd_v4_kernel(const float* __restrict__ enc_out, const fl
 }
 
 // q(y|x) head forward, one row per thread (K <= 16)
-__global__ void head_y_fwd_row_kernel(const float* __restrict__ logits, const float* __restrict__ u, int B, int K, float inv_T,
+__global__ void head_y_fwd_row_kernel(const float* __restrict__ logits, const float* __restrict__ gum, int B, int K, float inv_T,
                                       float inv_bg, float* __restrict__ y_f32, bf16* __restrict__ y_act, int ld_yact,
                                       float* __restrict__ acc) {
   griddep_wait();
@@ -513,7 +524,7 @@ __global__ void head_y_fwd_row_kernel(const float* __restrict__ logits, const fl
       l[k] = -INFINITY; a[k] = -INFINITY;
       if (k < K) {
         l[k] = logits[(int64_t)row * K + k];
-        a[k] = u ? (l[k] - logf(-logf(u[(int64_t)row * K + k]))) * inv_T : l[k];
+        a[k] = gum ? (l[k] + gum[(int64_t)row * K + k]) * inv_T : l[k];
       }
       ml = fmaxf(ml, l[k]); ma = fmaxf(ma, a[k]);
     }

@@ -183,6 +183,13 @@ GMVAE_API int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, floa
  * device memory) for the following steps; null switches it off. */
 GMVAE_API int gmvae_debug_chain_trace(gmvae_handle* h, long long* trace, int cta);
 
+/* Test hooks: per-job counters of the first chained launch of a step, summed over all CTAs (8 uint64 per job, globaltimer ns:
+ * first start, last end, dependency wait, MMA issue time, epilogue time, accumulator wait, tiles, accumulator-free wait; the
+ * caller presets [0] of every job to ~0 and the rest to 0; 40 jobs), and the descriptions of those jobs (8 ints per job:
+ * epilogue kind, M, N, k-blocks, tiles, splits, tile width, dependencies; returns the number of jobs). */
+GMVAE_API int gmvae_debug_chain_jobstat(gmvae_handle* h, unsigned long long* stat);
+GMVAE_API int gmvae_debug_chain_jobs(gmvae_handle* h, int* out, int cap_jobs);
+
 /* Per-launch profile: with profiling on, a CUDA event is recorded after every launch of the
  * (eager) step; read() returns the summed device time and launch count per kernel class:
  * 0 tcgen05 GEMM fwd/dgrad, 1 tcgen05 GEMM wgrad, 2 SIMT GEMM, 3 distribution heads,

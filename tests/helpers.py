@@ -16,6 +16,12 @@ CONFIGS = {
     "nohidden_gmvae": dict(model="gmvae", latent_size=16, hidden_sizes=[], mixture_components=4, batch=19, data_size=64),
     # the run_train.sh example shape (bin/run_train.sh:5-11): z=128, h=512 x 1, batch 64
     "run_train_sh": dict(model="gmvae", latent_size=128, hidden_sizes=[512], mixture_components=10, batch=64),
+    # BASELINE.json configs[4] (cfg5) at a batch the oracle finishes in seconds: K=50 > 16 leaves the fused y head
+    # (engine.cu forward_encoder / head_y_*_kernel), Z=128 > 64 leaves the z row job of the chained kernel
+    "cfg5_small": dict(model="gmvae", latent_size=128, hidden_sizes=[1024, 1024], mixture_components=50, batch=200),
+    # 16 < K <= 32, nothing a multiple of a tile, more than one 128-row block
+    "k20_ragged": dict(model="gmvae", latent_size=40, hidden_sizes=[96, 72], mixture_components=20, batch=150, data_size=200),
+    "k17_gmp": dict(model="vae_gmp", latent_size=20, hidden_sizes=[64], mixture_components=17, batch=130, data_size=96),
 }
 
 
@@ -55,7 +61,7 @@ def grad_errors(engine, grads_ref):
     return out
 
 
-def run_parity(cfg, precision, seed=2024, rounding_model=None, objective="reference"):
+def run_parity(cfg, precision, seed=2024, rounding_model=None, objective="reference", want_ref=False):
     """Returns (loss-term errors, per-tensor gradient errors) of the CUDA step against the oracle.
     With `rounding_model` the oracle restates the bf16 storage points of the CUDA path."""
     spec = make_spec(cfg)
@@ -67,12 +73,39 @@ def run_parity(cfg, precision, seed=2024, rounding_model=None, objective="refere
     loss = eng.forward_backward(x, eps=eps, gumbel_u=u)
     torch.cuda.synchronize()
     t = loss.detach().cpu().tolist()
-    terr = {"loss": rel(t[0], terms_ref["loss"].item()), "nll": rel(t[1], terms_ref["nll"].item()),
-            "kl_div_z": abs(t[2] - terms_ref["kl_div_z"].item()) / max(abs(terms_ref["kl_div_z"].item()), 1.0),
-            "nent": abs(t[3] - terms_ref["nent"].item()) / max(abs(terms_ref["nent"].item()), 1.0)}
+    terr = term_errors(t, terms_ref, spec)
     gerr = grad_errors(eng, grads_ref)
     eng.close()
+    if want_ref:
+        return terr, gerr, {k: terms_ref[k].item() for k in ("loss", "nll", "kl_div_z", "nent")}
     return terr, gerr
+
+
+def term_errors(t, terms_ref, spec):
+    """Relative error of [loss, nll, kl_div_z, nent] against the oracle's terms.  All four are TRUE relative errors
+    |t - ref| / |ref|.  (nent of the VAE models is identically 0 on both sides: error 0.)"""
+    out = {}
+    for i, k in enumerate(("loss", "nll", "kl_div_z", "nent")):
+        ref = terms_ref[k].item() if hasattr(terms_ref[k], "item") else float(terms_ref[k])
+        out[k] = 0.0 if (ref == 0.0 and t[i] == 0.0) else abs(t[i] - ref) / max(abs(ref), 1e-30)
+    return out
+
+
+KL_ABS_FLOOR = 1.0   # nats
+
+
+def bf16_term_ok(terr, terms_ref, tol=2e-3):
+    """The bf16 bar on the loss terms, stated explicitly: loss, nll and nent within TRUE relative `tol` of the exact fp64
+    oracle; kl_div_z within `tol` * max(|kl_div_z|, 1 nat).  kl_div_z = mean_b[log q(z) - log p(z)] is a difference of two
+    log-densities of ~Z nats each and is 0.1-0.5 nats at fresh weights, so below 1 nat the bar is ABSOLUTE (2e-3 nats,
+    i.e. 4e-6 of the loss it is a summand of); the true relative error is what `terr` holds and what the tests report."""
+    bad = {}
+    for k, v in terr.items():
+        ref = abs(float(terms_ref[k]))
+        lim = tol * max(ref, KL_ABS_FLOOR) / max(ref, 1e-30) if k == "kl_div_z" else tol
+        if v >= lim:
+            bad[k] = (v, lim)
+    return bad
 
 
 # --------------------------------------------------------------------------- bf16 rounding model

@@ -62,7 +62,11 @@ def test_cuda_step_matches_golden(path, precision):
     tol = 1e-5 if precision == "fp32" else 2e-3
     for i, k in enumerate(("loss", "nll", "kl_div_z", "nent")):
         ref = rec["terms"][k]
-        assert abs(t[i] - ref) / max(abs(ref), 1.0) < tol, (k, t[i], ref)
+        if ref == 0.0 and t[i] == 0.0:
+            continue
+        # true relative error; bf16 kl_div_z below one nat: absolute 2e-3 nats (tests/helpers.bf16_term_ok)
+        floor = 1.0 if (precision == "bf16" and k == "kl_div_z") else 1e-30
+        assert abs(t[i] - ref) / max(abs(ref), floor) < tol, (k, t[i], ref)
     if precision == "fp32":
         grads = eng.gradients()
         for n, v in rec["grad_norms"].items():

@@ -18,7 +18,7 @@ import torch  # noqa: E402
 from oracle import gmvae_oracle as O  # noqa: E402
 from tests.helpers import CONFIGS, make_spec, perturbed_params  # noqa: E402
 
-CASES = ["tiny_vae", "tiny_gmp", "tiny_gmvae", "nohidden_gmvae", "cfg1", "cfg2", "cfg3", "run_train_sh"]
+CASES = ["tiny_vae", "tiny_gmp", "tiny_gmvae", "nohidden_gmvae", "cfg1", "cfg2", "cfg3", "run_train_sh", "cfg5_small", "k20_ragged", "k17_gmp"]
 
 
 def main():
