@@ -59,7 +59,14 @@ SYMBOLS = {
     "gmvae_encode": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "gmvae_decode": (_I, [_P, _P, _I, _P, _P]),
     "gmvae_prior_table": (_I, [_P, _P, _P, _P]),
+    "gmvae_condition": (_I, [_P, _I, _P, _P, _I, _P, _P, _P]),
+    "gmvae_dist_normal_sample": (_I, [_P, _P, _P, _I64, _P, _P]),
+    "gmvae_dist_normal_log_prob": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "gmvae_dist_bernoulli_log_prob": (_I, [_P, _P, _I, _I, _P, _P]),
+    "gmvae_dist_bernoulli_mean": (_I, [_P, _I64, _P, _P]),
+    "gmvae_dist_relaxed_sample": (_I, [_P, _P, _I, _I, C.c_float, _P, _P]),
     "gmvae_binarize": (_I, [_P, _P, _I64, _P, _I, C.c_uint64, _P, _P]),
+    "gmvae_unpack_bits": (_I, [_P, _P, _I, _P, _P]),
     "gmvae_debug_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "gmvae_debug_noise": (_I, [_P, _P, _I64, _P, _I64, _P]),
     "gmvae_debug_chain_trace": (_I, [_P, _P, _I]),
@@ -85,13 +92,27 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        try:
-            _build.build()
-        except Exception as e:  # no nvcc / compile error: the product cannot run
-            raise RuntimeError(
-                f"libgmvae_b200.so is missing and could not be built ({e}); there is no CPU fallback. "
-                f"Run `python -m gmvae_b200.build`.") from e
+    # (Re)build when the library is missing or older than a source file -- under a file lock, so that the ranks of one
+    # torchrun launch do not race nvcc on the same output.  A stale library with no nvcc around is loaded as it is.
+    if _build.needs_build():
+        import fcntl
+        import shutil
+        have_nvcc = os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or shutil.which("nvcc")
+        if have_nvcc or not os.path.exists(path):
+            try:
+                with open(path + ".lock", "w") as lk:
+                    fcntl.flock(lk, fcntl.LOCK_EX)
+                    try:
+                        if _build.needs_build():
+                            _build.build()
+                    finally:
+                        fcntl.flock(lk, fcntl.LOCK_UN)
+            except Exception as e:  # no nvcc / compile error: the product cannot run
+                if not os.path.exists(path):
+                    raise RuntimeError(
+                        f"libgmvae_b200.so is missing and could not be built ({e}); there is no CPU fallback. "
+                        f"Run `python -m gmvae_b200.build`.") from e
+                raise
     try:
         import torch  # noqa: F401  (loads the bundled libnccl/libcudart the library links against)
     except Exception:

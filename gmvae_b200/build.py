@@ -19,12 +19,30 @@ def nccl_dirs():
     return os.path.join(base, "include"), os.path.join(base, "lib")
 
 
+HASH = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the sources and headers the library is built from (content, not mtime: the snapshot that carries the
+    built library to the GPU box does not keep timestamps in order)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.path.join(CSRC, s) for s in SOURCES + HEADERS):
+        if os.path.exists(f):
+            h.update(os.path.basename(f).encode())
+            with open(f, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    files = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in files)
+    try:
+        with open(HASH) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -45,6 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libgmvae_b200.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
+    with open(HASH, "w") as fh:
+        fh.write(source_hash())
     return LIB
 
 

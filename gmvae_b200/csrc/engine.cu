@@ -53,8 +53,10 @@ long long* g_trace = nullptr;
 
 int g_reserved_sms = 0;   // SMs left to the NCCL kernels while a data-parallel step is running
 
+int current_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 ? 0 : dev % 64; }
 int num_sms() {
-  static int n = 0;
+  static int n_by_dev[64] = {};
+  int& n = n_by_dev[current_device()];
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -135,7 +137,7 @@ enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8
                                reading the bf16 activation through TMA, kept as an experiment */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
 enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
-       PC_COUNT = 7 };
+       PC_COMM = 7, PC_COUNT = 8 };
 
 }  // namespace gmvae
 
@@ -160,6 +162,8 @@ struct gmvae_handle {
   ShadowEntry* shadow_dev = nullptr; int shadow_tiles = 0;
   DeviceState* state = nullptr;
   uint64_t seed_host = 0;                // host copy of state->seed (it changes only through gmvae_set_seed)
+  uint64_t draws = 0;                    // noise draws made outside training steps (mixed into the Philox key, kernels.cuh fill_noise_body)
+  bool in_train_step = false;
   int64_t launches = 0;
   int debug_flags = 0;
   // per-launch CUDA-event profile (off by default; bench.py turns it on for a few eager steps)
@@ -410,7 +414,8 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain_flush_after = false;
   h->last_gemm_chained = false;
   if (h->chain.njobs == 0) return 0;
-  static bool attr_set = false;
+  static bool attr_set_by_dev[64] = {};                      // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_by_dev[tc::current_device()];
   if (!attr_set) {
     GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
     GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
@@ -860,6 +865,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
   {
     const int64_t n = (int64_t)B * D;
     const bool need_noise = !eps || (gm && !u);
+    const uint64_t draw = (need_noise && !h->in_train_step) ? ++h->draws : 0;
     float* e = h->buf<float>("eps"); float* uu = gm ? h->buf<float>("u") : nullptr;
     const int64_t ne = eps ? 0 : (int64_t)B * Z, nu = (gm && !u) ? (int64_t)B * K : 0;
     const int64_t q = (ne + 3) / 4 + (nu + 3) / 4;
@@ -867,7 +873,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
     if (D % 16 == 0 && need_noise) {      // image conversion and noise in one launch
       const unsigned xb = (unsigned)((n / 16 + 255) / 256), nb = (unsigned)((q + 255) / 256);
       GM_CHECK_CUDA(launch_k(prologue_kernel<A>, dim3(xb + nb), dim3(256), 0, st, false, x_u8, x_act, n, (int)xb, e, ne, uu, nu,
-                             (const DeviceState*)h->state, (uint64_t)h->rank));
+                             (const DeviceState*)h->state, (uint64_t)h->rank, draw));
       GM_LAUNCHED(h, st, PC_MISC);
     } else {
       if (D % 16 == 0) GM_CHECK_CUDA(launch_k(convert_x_kernel<A>, dim3((unsigned)((n / 16 + 255) / 256)), dim3(256), 0, st, false, x_u8, x_act, n));
@@ -875,7 +881,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
       GM_LAUNCHED(h, st, PC_MISC);
       if (need_noise) {
         GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, uu, nu,
-                               (const DeviceState*)h->state, (uint64_t)h->rank, 1));
+                               (const DeviceState*)h->state, (uint64_t)h->rank, 1, draw));
         GM_LAUNCHED(h, st, PC_MISC);
       }
     }
@@ -1247,7 +1253,7 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
     float* e = h->buf<float>("eps");
     const int64_t ne = (int64_t)B * K * Z, q = (ne + 3) / 4;
     GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, st, true, e, ne, (float*)nullptr, (int64_t)0,
-                           (const DeviceState*)h->state, (uint64_t)h->rank, 0));
+                           (const DeviceState*)h->state, (uint64_t)h->rank, 0, h->in_train_step ? (uint64_t)0 : ++h->draws));
     GM_LAUNCHED(h, st, PC_MISC);
     eps = e;
   }
@@ -1325,7 +1331,8 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
       const int blocks = std::max(1, std::min(2 * tc::num_sms(), (R + lanes - 1) / lanes));
       const size_t smem = (size_t)(2 * 256 + K * 2 * Z) * sizeof(float);
       GM_REQUIRE(smem <= 200 * 1024, "objective=marginal: mixture_components * latent_size too large for the prior-table gradient tile");
-      static size_t smem_set = 0;
+      static size_t smem_set_by_dev[64] = {};
+      size_t& smem_set = smem_set_by_dev[tc::current_device()];
       if (smem > smem_set) {
         GM_CHECK_CUDA(cudaFuncSetAttribute(head_z_m_bwd_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
@@ -1341,7 +1348,8 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
       const int col_blocks = (H0 + 63) / 64;
       int spb = std::max(4, (nb * col_blocks + 2 * tc::num_sms() - 1) / (2 * tc::num_sms()));
       dim3 grid(col_blocks, (nb + spb - 1) / spb);
-      static bool attr = false;
+      static bool attr_by_dev[64] = {};
+      bool& attr = attr_by_dev[tc::current_device()];
       if (!attr) {
         GM_CHECK_CUDA(cudaFuncSetAttribute(reduce_k_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * HEAD_MAXK * 64 * (int)sizeof(float)));
         attr = true;
@@ -1376,6 +1384,19 @@ static int refresh_shadows(gmvae_handle* h, cudaStream_t st) {
   }
   return 0;
 }
+
+// Every entry point that enqueues work makes the handle's device current for the duration of the call and restores the
+// caller's afterwards (a process may hold handles on several GPUs).
+struct DeviceGuard {
+  int prev = -1, want = -1;
+  explicit DeviceGuard(const gmvae_handle* h) {
+    if (!h) return;
+    want = h->cfg.device;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
 
 static int check_ready(const gmvae_handle* h) {
   GM_REQUIRE(h != nullptr, "null handle");
@@ -1414,9 +1435,9 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   cudaDeviceProp prop;
   GM_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   GM_REQUIRE(prop.major == 10, "libgmvae_b200 is built for sm_100a (B200) only");
-  GM_CHECK_CUDA(cudaSetDevice(cfg->device));
   gmvae_handle* h = new gmvae_handle();
   h->cfg = *cfg;
+  DeviceGuard dev_guard(h);
   const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
   h->debug_flags = dbg ? atoi(dbg) : 0;
   g_use_pdl = !(h->debug_flags & DBG_NO_PDL);
@@ -1455,6 +1476,7 @@ size_t gmvae_workspace_bytes(const gmvae_handle* h) { return h ? h->ws_needed : 
 int64_t gmvae_launch_count(const gmvae_handle* h) { return h ? h->launches : -1; }
 
 int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, float* adam_v, void* workspace, size_t workspace_bytes) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && params && grads && adam_m && adam_v && workspace, "null argument");
   GM_REQUIRE(workspace_bytes >= h->ws_needed, "workspace too small");
   GM_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(adam_m) && aligned16(adam_v), "buffers must be 16-byte aligned");
@@ -1488,12 +1510,14 @@ int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, floa
 }
 
 int gmvae_params_updated(gmvae_handle* h, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   return refresh_shadows(h, (cudaStream_t)stream);
 }
 
 int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
                            const float* gumbel_u, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   GM_REQUIRE(x_u8 != nullptr, "null input");
   GM_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "batch must be in [1, max_batch]");
@@ -1508,6 +1532,7 @@ int gmvae_forward_backward(gmvae_handle* h, const uint8_t* x_u8, int batch, int 
 }
 
 int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   GM_REQUIRE(loss_terms != nullptr, "null loss_terms");
   GM_CHECK_CUDA(launch_k(finalize_loss_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, false, (const float*)(h->grads + h->n_params), loss_terms)); GM_LAUNCHED(h, (cudaStream_t)stream, PC_MISC);
@@ -1530,11 +1555,13 @@ static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st) {
 }
 
 int gmvae_adam_step(gmvae_handle* h, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   return adam_step_impl(h, nullptr, (cudaStream_t)stream);
 }
 
 int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && step, "null argument");
   DeviceState s;
   GM_CHECK_CUDA(cudaMemcpyAsync(&s, h->state, sizeof(s), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -1543,6 +1570,7 @@ int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream) {
   return 0;
 }
 int gmvae_set_step(gmvae_handle* h, int64_t step, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h, "null argument");
   long long v = step;
   GM_CHECK_CUDA(cudaMemcpyAsync(&h->state->step, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -1550,6 +1578,7 @@ int gmvae_set_step(gmvae_handle* h, int64_t step, void* stream) {
   return 0;
 }
 int gmvae_set_seed(gmvae_handle* h, uint64_t seed) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h, "null argument");
   unsigned long long v = seed;
   GM_CHECK_CUDA(cudaMemcpy(&h->state->seed, &v, sizeof(v), cudaMemcpyHostToDevice));
@@ -1648,6 +1677,7 @@ static int peer_allreduce(gmvae_handle* h, cudaStream_t st) {
 }
 
 int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   if (h->peer_ready && h->world > 1) return peer_allreduce(h, (cudaStream_t)stream);
   if (!h->comm || h->world == 1) return 0;
@@ -1664,14 +1694,18 @@ int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
   }
   ncclResult_t r = ncclAllReduce(h->grads, h->grads, (size_t)total, ncclFloat, ncclSum, h->comm, st);
   if (r != ncclSuccess) { set_error(std::string("ncclAllReduce: ") + ncclGetErrorString(r)); return -5; }
-  h->launches++;
+  GM_LAUNCHED(h, st, PC_COMM);                               // the exchange step is in-stream: its interval is the exposed communication
   return 0;
 }
 
 int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps, const float* gumbel_u,
                      float* loss_terms, void* stream) {
+  DeviceGuard dev_guard(h);
+  GM_REQUIRE(h != nullptr, "null handle");
   h->overlap_comm = h->comm != nullptr && h->world > 1 && (h->debug_flags & DBG_COMM_OVERLAP);
+  h->in_train_step = true;
   int r = gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream);
+  h->in_train_step = false;
   if (r == 0) r = gmvae_allreduce_grads(h, stream);
   h->overlap_comm = false;
   GM_TRY(r);
@@ -1680,6 +1714,7 @@ int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global
 
 int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
                              const float* gumbel_u, float* loss_terms, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   cudaStream_t st = (cudaStream_t)stream;
   GM_REQUIRE(st != nullptr, "graph capture needs a non-default stream");
@@ -1699,6 +1734,7 @@ int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, in
   return 0;
 }
 int gmvae_step_graph_launch(gmvae_handle* h, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && h->graph_exec, "no captured graph");
   GM_CHECK_CUDA(cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream));
   return 0;
@@ -1738,10 +1774,115 @@ static int decode_impl(gmvae_handle* h, const float* z, int n, float* x_mean, cu
   return 0;
 }
 
+// ConditionalNormal / ConditionalBernoulli / ConditionalCategorical .condition(tensor_list) (base.py:63-72, 130-135, 193-198):
+// concat(inputs) -> MLP -> distribution parameters, on caller tensors, through the same GEMM kernels as the step.
+template <typename A>
+static int condition_impl(gmvae_handle* h, int which, const float* in1, const float* in2, int n, float* out_a, float* out_b, cudaStream_t st) {
+  const gmvae_config& c = h->cfg;
+  const int D = h->D, Z = h->Z, K = h->K, nl = h->L;
+  const int Dp = ldp(D), Zp = ldp(Z), Kp = ldp(K);
+  const bool gm = c.model == GMVAE_MODEL_GMVAE;
+  auto hid_ld = [&](int i) { return (int64_t)ldp(h->hidden[i]); };
+  auto to_act = [&](const float* src, int cols, A* dst, int ld) -> int {
+    const int64_t cnt = (int64_t)n * cols;
+    GM_CHECK_CUDA(launch_k(to_act_kernel<A>, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, false, src, n, cols, dst, ld));
+    GM_LAUNCHED(h, st, PC_MISC);
+    return 0;
+  };
+  auto normal_out = [&](const float* outs) -> int {
+    const int64_t cnt = (int64_t)n * Z;
+    GM_CHECK_CUDA(launch_k(normal_params_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, true, outs, n, Z, c.raw_sigma_bias,
+                           c.sigma_min, out_a, out_b));
+    GM_LAUNCHED(h, st, PC_HEADS);
+    return 0;
+  };
+  // last layer of an MLP into an fp32 matrix
+  auto last_layer = [&](const Mlp& m, const MlpBufs<A>& b, const A* in0, int64_t ld0, int in0_cols, float* out, int out_cols) -> int {
+    const Linear& l = m.layers[nl - 1];
+    EpiStore<float> epi{out, (int64_t)out_cols, h->params + l.b_off, nullptr, 0, 0, 1.f};
+    return lin_fwd<A>(h, nl == 1 ? in0 : b.hid[nl - 2], nl == 1 ? ld0 : hid_ld(nl - 2), n, view(h, l, 0, nl == 1 ? in0_cols : -1), epi, st);
+  };
+  if (which == GMVAE_COND_DECODER) {                          // logits = MLP(z) + bias_init
+    A* z_act = h->buf<A>("z_act");
+    MlpBufs<A> dec = mlp_bufs<A>(h, h->decoder);
+    GM_TRY(to_act(in1, Z, z_act, Zp));
+    GM_TRY(mlp_hidden_fwd<A>(h, h->decoder, dec, z_act, Zp, Z, n, 0, st));
+    GM_TRY(last_layer(h->decoder, dec, z_act, Zp, Z, out_a, D));
+    if (c.gen_bias_init != 0.f) {
+      const int64_t cnt = (int64_t)n * D;
+      GM_CHECK_CUDA(launch_k(add_scalar_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, st, true, out_a, cnt, c.gen_bias_init));
+      GM_LAUNCHED(h, st, PC_MISC);
+    }
+    return 0;
+  }
+  A* x_act = h->buf<A>("x_act");
+  if (which == GMVAE_COND_ENCODER_Y) {                        // logits of q(y|x)
+    GM_REQUIRE(gm, "encoder_y exists in the GMVAE only");
+    MlpBufs<A> ey = mlp_bufs<A>(h, h->encoder_y);
+    GM_TRY(to_act(in1, D, x_act, Dp));
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder_y, ey, x_act, Dp, D, n, 0, st));
+    return last_layer(h->encoder_y, ey, x_act, Dp, D, out_a, K);
+  }
+  if (which == GMVAE_COND_PRIOR_GMM) {                        // p(z|y): one linear K -> 2Z
+    GM_REQUIRE(gm, "prior_gmm exists in the GMVAE only");
+    A* y_act = h->buf<A>("y_act"); float* prior_out = h->buf<float>("prior_out");
+    GM_REQUIRE(prior_out != nullptr, "gmvae_condition(prior_gmm) needs a handle created with objective=reference");
+    GM_TRY(to_act(in1, K, y_act, Kp));
+    const Linear& l = h->prior_gmm.layers[0];
+    EpiStore<float> epi{prior_out, (int64_t)2 * Z, h->params + l.b_off, nullptr, 0, 0, 1.f};
+    GM_TRY(lin_fwd<A>(h, y_act, Kp, n, view(h, l), epi, st));
+    return normal_out(prior_out);
+  }
+  GM_REQUIRE(which == GMVAE_COND_ENCODER, "unknown conditional distribution");
+  MlpBufs<A> enc = mlp_bufs<A>(h, h->encoder);
+  float* enc_out = h->buf<float>("enc_out");
+  GM_TRY(to_act(in1, D, x_act, Dp));
+  if (!gm) {                                                  // q(z|x)
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, n, 0, st));
+    GM_TRY(last_layer(h->encoder, enc, x_act, Dp, D, enc_out, 2 * Z));
+    return normal_out(enc_out);
+  }
+  // q(z|x,y): [x,y] W = x W[:D] + y W[D:]  (no concat, base.py:66)
+  GM_REQUIRE(in2 != nullptr, "encoder_gmm takes (x, y)");
+  GM_REQUIRE(c.objective == GMVAE_OBJECTIVE_REFERENCE, "gmvae_condition(encoder_gmm) needs a handle created with objective=reference");
+  A* y_act = h->buf<A>("y_act");
+  GM_TRY(to_act(in2, K, y_act, Kp));
+  const Linear& enc_l0 = h->encoder.layers[0];
+  LinView Lx = view(h, enc_l0, 0, D), Ly = view(h, enc_l0, D, K);
+  const bool last0 = nl == 1;
+  const bool two_seg = tc_ok_fwd<A>(h, x_act, Dp, Lx) && tc_ok_fwd<A>(h, y_act, Kp, Ly) && !(h->debug_flags & DBG_NO_TWO_SEG);
+  if (two_seg) {
+    if (last0) {
+      EpiStore<float> epi{enc_out, (int64_t)2 * Z, Lx.b, nullptr, 0, 0, 1.f};
+      GM_TRY(lin_fwd<A>(h, x_act, Dp, n, Lx, epi, st, y_act, Kp, &Ly));
+    } else {
+      EpiStore<A> epi{enc.hid[0], hid_ld(0), Lx.b, nullptr, 0, 1, 1.f};
+      GM_TRY(lin_fwd<A>(h, x_act, Dp, n, Lx, epi, st, y_act, Kp, &Ly));
+    }
+  } else {
+    float* pre = h->buf<float>("pre_y");
+    EpiStore<float> e0{pre, (int64_t)enc_l0.out, Lx.b, nullptr, 0, 0, 1.f};
+    GM_TRY((lin_fwd<A, EpiStore<float>, false>(h, y_act, Kp, n, Ly, e0, st)));
+    if (last0) {
+      EpiStore<float, EPI_ADDEND> epi{enc_out, (int64_t)2 * Z, nullptr, pre, (int64_t)enc_l0.out, 0, 1.f};
+      GM_TRY((lin_fwd<A, EpiStore<float, EPI_ADDEND>, false>(h, x_act, Dp, n, Lx, epi, st)));
+    } else {
+      EpiStore<A, EPI_ADDEND> epi{enc.hid[0], hid_ld(0), nullptr, pre, (int64_t)enc_l0.out, 1, 1.f};
+      GM_TRY((lin_fwd<A, EpiStore<A, EPI_ADDEND>, false>(h, x_act, Dp, n, Lx, epi, st)));
+    }
+  }
+  if (!last0) {
+    GM_TRY(mlp_hidden_fwd<A>(h, h->encoder, enc, x_act, Dp, D, n, 1, st));
+    GM_TRY(last_layer(h->encoder, enc, x_act, Dp, D, enc_out, 2 * Z));
+  }
+  return normal_out(enc_out);
+}
+
 extern "C" {
 
 int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, const float* eps, const float* gumbel_u, float* logits_y, float* z_mean,
                  float* z_sample, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   GM_REQUIRE(x_u8 && z_mean && z_sample, "null argument");
   GM_REQUIRE(batch > 0 && batch <= h->cfg.max_batch, "batch must be in [1, max_batch]");
@@ -1749,7 +1890,46 @@ int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, const float* e
   if (h->bf16_mode()) return encode_impl<bf16>(h, x_u8, batch, eps, gumbel_u, logits_y, z_mean, z_sample, (cudaStream_t)stream);
   return encode_impl<float>(h, x_u8, batch, eps, gumbel_u, logits_y, z_mean, z_sample, (cudaStream_t)stream);
 }
+int gmvae_condition(gmvae_handle* h, int which, const float* in1, const float* in2, int n, float* out_a, float* out_b, void* stream) {
+  DeviceGuard dev_guard(h);
+  GM_TRY(check_ready(h));
+  GM_REQUIRE(in1 && out_a, "null argument");
+  GM_REQUIRE(n > 0 && n <= h->cfg.max_batch, "n must be in [1, max_batch]");
+  GM_REQUIRE(which >= 0 && which <= 3, "unknown conditional distribution");
+  GM_REQUIRE(out_b || which == GMVAE_COND_DECODER || which == GMVAE_COND_ENCODER_Y, "a ConditionalNormal returns (mu, sigma): out_b is null");
+  if (h->bf16_mode()) return condition_impl<bf16>(h, which, in1, in2, n, out_a, out_b, (cudaStream_t)stream);
+  return condition_impl<float>(h, which, in1, in2, n, out_a, out_b, (cudaStream_t)stream);
+}
+// sample / log_prob / mean of the distribution objects the Conditional* classes return (TFP semantics)
+int gmvae_dist_normal_sample(const float* mu, const float* sigma, const float* eps, int64_t n, float* out, void* stream) {
+  GM_REQUIRE(mu && sigma && eps && out && n > 0, "bad argument");
+  GM_CHECK_CUDA(launch_k(dist_map_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, 0, mu, sigma, eps, n, out));
+  return 0;
+}
+int gmvae_dist_normal_log_prob(const float* mu, const float* sigma, const float* z, int n, int d, float* out, void* stream) {
+  GM_REQUIRE(mu && sigma && z && out && n > 0 && d > 0, "bad argument");
+  GM_CHECK_CUDA(launch_k(dist_row_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, false, 0, mu, sigma, z, n, d, 1.f, out));
+  return 0;
+}
+int gmvae_dist_bernoulli_log_prob(const float* logits, const float* x, int n, int d, float* out, void* stream) {
+  GM_REQUIRE(logits && x && out && n > 0 && d > 0, "bad argument");
+  GM_CHECK_CUDA(launch_k(dist_row_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, false, 1, logits, (const float*)nullptr, x, n, d, 1.f, out));
+  return 0;
+}
+int gmvae_dist_bernoulli_mean(const float* logits, int64_t n, float* out, void* stream) {
+  GM_REQUIRE(logits && out && n > 0, "bad argument");
+  GM_CHECK_CUDA(launch_k(dist_map_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, 1, logits, (const float*)nullptr,
+                         (const float*)nullptr, n, out));
+  return 0;
+}
+int gmvae_dist_relaxed_sample(const float* logits, const float* u, int n, int k, float temperature, float* out, void* stream) {
+  GM_REQUIRE(logits && u && out && n > 0 && k > 0 && temperature > 0.f, "bad argument");
+  GM_CHECK_CUDA(launch_k(dist_row_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, false, 2, logits, (const float*)nullptr, u, n, k,
+                         1.f / temperature, out));
+  return 0;
+}
 int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   GM_REQUIRE(z && x_mean, "null argument");
   const int cap = h->cfg.objective == GMVAE_OBJECTIVE_MARGINAL ? h->chunk_samples * h->K : h->cfg.max_batch;
@@ -1758,6 +1938,7 @@ int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* st
   return decode_impl<float>(h, z, n, x_mean, (cudaStream_t)stream);
 }
 int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
   GM_REQUIRE(mu && sigma, "null argument");
   const int K = h->K, Z = h->Z;
@@ -1770,13 +1951,14 @@ int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream) {
 }
 
 int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int64_t n_u, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h, "null argument");
   if (!eps) n_eps = 0;
   if (!u) n_u = 0;
   int64_t q = (n_eps + 3) / 4 + (n_u + 3) / 4;
   if (q == 0) return 0;
   GM_CHECK_CUDA(launch_k(fill_noise_kernel, dim3((unsigned)((q + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, eps, n_eps, u, n_u,
-                         (const DeviceState*)h->state, (uint64_t)h->rank, 0));
+                         (const DeviceState*)h->state, (uint64_t)h->rank, 0, ++h->draws));
   return 0;
 }
 
@@ -1785,6 +1967,7 @@ int gmvae_debug_noise(gmvae_handle* h, float* eps, int64_t n_eps, float* u, int6
 // each in [0, n_rows)) or, without an index, from row r.  Uniforms: Philox keyed by (seed, draw, rank, element).
 int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, const int64_t* row_index, int batch, uint64_t draw,
                    uint8_t* x_u8, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && h->state, "null handle");
   GM_REQUIRE(batch >= 0 && n_rows >= 0, "negative size");
   if (batch == 0) return 0;
@@ -1806,6 +1989,18 @@ int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, 
   philox_schedule(binarize_key(h->seed_host, draw), rk);
   GM_CHECK_CUDA(launch_k(binarize_kernel, dim3(blocks), dim3(BINARIZE_THREADS), 0, (cudaStream_t)stream, false, intensities, row_index, D,
                          n_out, rk, (uint64_t)h->rank, mode, x_u8));
+  h->launches++;
+  return 0;
+}
+
+// Bit-packed binary images (numpy.packbits order, ceil(D/8) bytes per row) -> the [batch, D] {0,1} bytes the step reads.
+int gmvae_unpack_bits(gmvae_handle* h, const uint8_t* packed, int batch, uint8_t* x_u8, void* stream) {
+  DeviceGuard dev_guard(h);
+  GM_REQUIRE(h && packed && x_u8, "null argument");
+  GM_REQUIRE(batch > 0, "batch must be positive");
+  const int D = h->cfg.data_size, row_bytes = (D + 7) / 8;
+  const int64_t n = (int64_t)batch * row_bytes;
+  GM_CHECK_CUDA(launch_k(unpack_bits_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, false, packed, n, row_bytes, D, x_u8));
   h->launches++;
   return 0;
 }
@@ -1842,7 +2037,7 @@ int gmvae_profile_enable(gmvae_handle* h, int on) {
 }
 int gmvae_profile_read(gmvae_handle* h, double* ms_by_class, int64_t* launches_by_class, int n_classes) {
   GM_REQUIRE(h && ms_by_class && launches_by_class, "null argument");
-  GM_REQUIRE(n_classes >= PC_COUNT, "need room for 7 classes");
+  GM_REQUIRE(n_classes >= PC_COUNT, "need room for 8 classes");
   for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0; launches_by_class[i] = 0; }
   if (h->marks.empty()) return 0;
   GM_CHECK_CUDA(cudaEventSynchronize(h->marks.back().first));
@@ -1867,6 +2062,7 @@ __global__ void dbg_to_bf16(const float* in, bf16* out, int64_t rows, int64_t co
 
 int gmvae_debug_gemm(gmvae_handle* h, int impl, int transA, int transB, int M, int N, int K, const float* A, const float* B,
                      float* C, int split_k, void* stream) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && A && B && C, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   GM_CHECK_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * 4, st));

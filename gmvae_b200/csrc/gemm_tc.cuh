@@ -137,6 +137,48 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
                : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a 2-CTA cluster (the two SMs of a TPC) run ONE 256-row MMA -------------------
+// Each CTA holds its 128 rows of A, HALF of the B tile's columns and its 128 rows of the accumulator (own TMEM); the leader
+// (cluster rank 0) issues the instruction for both.  What it buys here: a 256 x 256 x 64 step needs 32 KB of operands per SM
+// instead of 48 KB -- the main loop of the chained kernel is bound by the ~72 GB/s each SM gets from L2, not by the tensor pipe.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose transaction bytes are counted on the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint64_t adesc, uint64_t bdesc, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on `bar` (same offset) in BOTH CTAs of the pair when every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"; same bit layout as
 // cute::UMMA::SmemDescriptor): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48)
@@ -418,13 +460,15 @@ struct Operand {
 };
 
 int num_sms();
+int current_device();
 extern int g_reserved_sms;
 extern long long* g_trace;   // device buffer of clock64 stamps of CTA 0 (test hook), normally null
 
 template <int BLOCK_N, bool A_MN, bool B_MN, class Epi>
 int launch_gemm_tc(const Operand& A1, const Operand& B1, const Operand* A2, const Operand* B2, int M, int N, int split_k,
                    const Epi& epi, cudaStream_t st, bool persistent = true) {
-  static bool attr_set = false;
+  static bool attr_set_by_dev[64] = {};              // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_by_dev[current_device()];
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, Epi>;
   if (!attr_set) {
     GM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BLOCK_N>()));

@@ -160,4 +160,24 @@ binarize_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ row
 }
 #endif
 
+// ---- bit-packed binary images ----------------------------------------------------------------------------------
+// The step's input is binary ({0,1} per pixel, runners.py:44-47), so the host side of a batch is 1 bit per pixel:
+// packed[b, j] holds pixels 8j .. 8j+7 of row b, most significant bit first (numpy.packbits order); D = 784 -> 98 bytes per
+// image instead of 784 over PCIe.  One thread per packed byte: one 8-byte store.
+__global__ void unpack_bits_kernel(const uint8_t* __restrict__ packed, int64_t n_bytes, int row_bytes, int D, uint8_t* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bytes) return;
+  const int64_t b = i / row_bytes; const int j = (int)(i - b * row_bytes);
+  const uint32_t v = packed[i];
+  uint8_t* dst = x + b * D + 8 * j;
+  if (8 * j + 8 <= D && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    // byte k of the output (little endian) = bit (7 - k) of v
+    const uint32_t lo = ((v >> 7) & 1u) | (((v >> 6) & 1u) << 8) | (((v >> 5) & 1u) << 16) | (((v >> 4) & 1u) << 24);
+    const uint32_t hi = ((v >> 3) & 1u) | (((v >> 2) & 1u) << 8) | (((v >> 1) & 1u) << 16) | ((v & 1u) << 24);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  } else {
+    for (int k = 0; k < 8 && 8 * j + k < D; ++k) dst[k] = (uint8_t)((v >> (7 - k)) & 1u);
+  }
+}
+
 }  // namespace gmvae

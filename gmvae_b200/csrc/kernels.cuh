@@ -68,8 +68,11 @@ __global__ void convert_x_rows_kernel(const uint8_t* __restrict__ x, T* __restri
 // q(y|x) head, which sits on the critical path of the step.
 __device__ __forceinline__ float gumbel_of(float u) { return -logf(-logf(u)); }
 __device__ __forceinline__ void fill_noise_body(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
-                                                const DeviceState* st, uint64_t rank_stream, int64_t block, int gumbel = 0) {
-  const uint64_t seed = st->seed, step = (uint64_t)st->step;
+                                                const DeviceState* st, uint64_t rank_stream, int64_t block, int gumbel = 0, uint64_t draw = 0) {
+  // keyed by (seed, global_step, draw, rank, element): `draw` is 0 inside a training step (the device step counter advances, so a
+  // captured graph draws fresh noise at every replay) and a host counter for every other call (encode, run_model, summaries), which
+  // do not advance the step -- the reference draws fresh noise on every sess.run
+  const uint64_t seed = st->seed ^ (draw * 0xD6E8FEB86659FD93ull), step = (uint64_t)st->step;
   int64_t i = block * blockDim.x + threadIdx.x;
   int64_t q_eps = (n_eps + 3) / 4, q_u = (n_u + 3) / 4;
   uint32_t r[4];
@@ -90,10 +93,10 @@ __device__ __forceinline__ void fill_noise_body(float* __restrict__ eps, int64_t
   }
 }
 __global__ void fill_noise_kernel(float* __restrict__ eps, int64_t n_eps, float* __restrict__ u, int64_t n_u,
-                                  const DeviceState* st, uint64_t rank_stream, int gumbel) {
+                                  const DeviceState* st, uint64_t rank_stream, int gumbel, uint64_t draw) {
   griddep_wait();
   griddep_launch();
-  fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, blockIdx.x, gumbel);
+  fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, blockIdx.x, gumbel, draw);
 }
 // injected uniforms (parity tests, run_model(..., gumbel_u=)) -> Gumbel noise
 __global__ void gumbel_from_u_kernel(const float* __restrict__ u, float* __restrict__ g, int64_t n) {
@@ -105,11 +108,11 @@ __global__ void gumbel_from_u_kernel(const float* __restrict__ u, float* __restr
 // first launch of a training step: blocks [0, x_blocks) convert the image bytes, the rest draw the noise
 template <typename T>
 __global__ void prologue_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int64_t n, int x_blocks, float* __restrict__ eps,
-                                int64_t n_eps, float* __restrict__ u, int64_t n_u, const DeviceState* st, uint64_t rank_stream) {
+                                int64_t n_eps, float* __restrict__ u, int64_t n_u, const DeviceState* st, uint64_t rank_stream, uint64_t draw) {
   griddep_wait();
   griddep_launch();
   if ((int)blockIdx.x < x_blocks) convert_x_body<T>(x, out, n, blockIdx.x);
-  else fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, (int64_t)blockIdx.x - x_blocks, 1);
+  else fill_noise_body(eps, n_eps, u, n_u, st, rank_stream, (int64_t)blockIdx.x - x_blocks, 1, draw);
 }
 
 // ---- q(y|x) head, forward (gmvae.py:238-240, 262-263; utils.py:165-170) ------------------------
@@ -651,6 +654,71 @@ __global__ void prior_params_kernel(const float* __restrict__ a, const float* __
   } else {
     mu[i] = 0.f; sigma[i] = 1.f;
   }
+}
+
+// ---- the callable distribution layer (base.py:63-83, 130-146, 193-209; gmvae_condition / gmvae_dist_*) -------------
+// [mu | raw] rows of a ConditionalNormal's MLP -> mu, sigma = max(softplus(raw + c), sigma_min)   (base.py:69-70)
+__global__ void normal_params_kernel(const float* __restrict__ outs, int n, int Z, float c, float sigma_min, float* __restrict__ mu,
+                                     float* __restrict__ sigma) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)n * Z) {
+    const int64_t b = i / Z; const int j = (int)(i % Z);
+    mu[i] = outs[b * 2 * Z + j];
+    sigma[i] = fmaxf(softplus_f(outs[b * 2 * Z + Z + j] + c), sigma_min);
+  }
+}
+__global__ void add_scalar_kernel(float* __restrict__ v, int64_t n, float s) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += s;
+}
+// op 0: MultivariateNormalDiag.sample      out[n,d] = a + b * c            (a = loc, b = scale_diag, c = eps)
+// op 1: Bernoulli.mean                     out[n,d] = sigmoid(a)           (a = logits)
+__global__ void dist_map_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, int64_t n,
+                                float* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = op == 0 ? fmaf(b[i], c[i], a[i]) : sigmoid_f(a[i]);
+}
+// One warp per row.
+// op 0: MultivariateNormalDiag.log_prob(z) = -1/2 sum ((z-mu)/sigma)^2 - sum log sigma - d/2 log 2 pi      (a = loc, b = scale_diag, c = z)
+// op 1: Independent(Bernoulli(logits),1).log_prob(x) = sum x l - max(l,0) - log1p(exp(-|l|))              (a = logits, c = x as float)
+// op 2: RelaxedOneHotCategorical.sample = softmax((logits + g)/T), g = -log(-log u)                       (a = logits, c = u, out [n,d])
+__global__ void dist_row_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, int n, int d,
+                                float inv_T, float* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int64_t base = (int64_t)row * d;
+  if (op == 2) {
+    float m = -INFINITY;
+    for (int j = lane; j < d; j += 32) m = fmaxf(m, (a[base + j] + gumbel_of(c[base + j])) * inv_T);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) s += expf((a[base + j] + gumbel_of(c[base + j])) * inv_T - m);
+    s = warp_sum(s);
+    for (int j = lane; j < d; j += 32) out[base + j] = expf((a[base + j] + gumbel_of(c[base + j])) * inv_T - m) / s;
+    return;
+  }
+  float acc = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    if (op == 0) {
+      const float t = (c[base + j] - a[base + j]) / b[base + j];
+      acc += -0.5f * t * t - logf(b[base + j]) - 0.9189385332046727f;
+    } else {
+      const float l = a[base + j];
+      acc += c[base + j] * l - softplus_f(l);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
 }
 
 // ---- VAE_GMP mixture prior (vae.py:231-244, 181): forward value and every gradient -------------

@@ -215,6 +215,22 @@ class Engine:
                                            out.data_ptr(), self._stream()), "gmvae_binarize")
         return out
 
+    def unpack_bits(self, packed: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Bit-packed binary images (numpy.packbits(x, axis=1): ceil(D/8) bytes per row, most significant bit first) ->
+        uint8 {0,1} [batch, D] on the device.  `packed` is a uint8 CUDA tensor [batch, ceil(D/8)]; pass the captured step's
+        input as `out` to refill it in place before `replay()`."""
+        rb = (self.data_size + 7) // 8
+        if packed.dtype != torch.uint8 or not packed.is_cuda or not packed.is_contiguous() or packed.dim() != 2 or packed.shape[1] != rb:
+            raise ValueError(f"packed must be a contiguous uint8 CUDA tensor [batch, {rb}]")
+        B = packed.shape[0]
+        if out is None:
+            out = torch.empty(B, self.data_size, dtype=torch.uint8, device=self.device)
+        elif out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous() or tuple(out.shape) != (B, self.data_size):
+            raise ValueError("out must be a contiguous uint8 CUDA tensor [batch, D]")
+        self._keep_in = [packed, out]
+        _lib.check(self.lib.gmvae_unpack_bits(self._h, packed.data_ptr(), B, out.data_ptr(), self._stream()), "gmvae_unpack_bits")
+        return out
+
     # ------------------------------------------------------------------ forward-only helpers
     def encode(self, x, eps=None, gumbel_u=None):
         """(logits_y or None, z_mean, z_sample): encoder side of the forward pass (gmvae.py:140-150, vae.py:105-112)."""
@@ -342,7 +358,7 @@ class Engine:
         _lib.check(self.lib.gmvae_peer_attach(self._h, b"".join(handles)), "gmvae_peer_attach")
         dist.barrier()
 
-    PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc"]
+    PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc", "comm"]
 
     def profile(self, on: bool):
         _lib.check(self.lib.gmvae_profile_enable(self._h, int(on)))

@@ -17,6 +17,25 @@ class GMVAE(_EngineBacked):
         self.mix_components = mix_components
         self.random_seed = random_seed
         self._init_backing()
+        prior_gmm._bind(self, base.COND_PRIOR_GMM); decoder._bind(self, base.COND_DECODER)
+        encoder_y._bind(self, base.COND_ENCODER_Y); encoder_gmm._bind(self, base.COND_ENCODER)
+
+    # ---- the distribution accessors of the reference (gmvae.py:49-107): each returns a distribution object ----
+    def prior_gmm(self, y):
+        """p(z | y): MultivariateNormalDiag [batch, latent_size] (gmvae.py:49-59)."""
+        return self._prior_gmm(y)
+
+    def decoder(self, z):
+        """p(x | z): independent Bernoulli [batch, data_size] (gmvae.py:62-72)."""
+        return self._decoder(z)
+
+    def encoder_y(self, x):
+        """q(y | x): RelaxedOneHotCategorical [batch, mix_components]; x is cast to float32 (gmvae.py:75-88)."""
+        return self._encoder_y(x)
+
+    def encoder_gmm(self, x, y):
+        """q(z | x, y): MultivariateNormalDiag [batch, latent_size]; x is cast to float32 (gmvae.py:91-106)."""
+        return self._encoder_gmm(x, y)
 
     def _engine_kwargs(self):
         eg, dec, ey = self._encoder_gmm, self._decoder, self._encoder_y

@@ -19,6 +19,7 @@ class VAE(_EngineBacked):
         self.mix_components = mix_components
         self.random_seed = random_seed
         self._init_backing()
+        decoder._bind(self, base.COND_DECODER); encoder._bind(self, base.COND_ENCODER)
 
     def _engine_kwargs(self):
         enc, dec = self._encoder, self._decoder
@@ -27,7 +28,17 @@ class VAE(_EngineBacked):
                     sigma_min=enc._sigma_min, raw_sigma_bias=enc._raw_sigma_bias, gen_bias_init=dec._bias_init)
 
     def prior(self):
-        return self._prior
+        """p(z) (vae.py:41-48): the standard normal MultivariateNormalDiag(0, I) (vae.py:247-250) or the learned
+        MixtureSameFamily(Categorical(mixture_logits), MVNDiag(loc, softplus(raw_scale_diag))) (vae.py:231-244)."""
+        return _Prior(self)
+
+    def decoder(self, z):
+        """p(x | z): independent Bernoulli [batch, data_size] (vae.py:51-61)."""
+        return self._decoder(z)
+
+    def encoder(self, x):
+        """q(z | x): MultivariateNormalDiag [batch, latent_size]; x is cast to float32 (vae.py:64-78)."""
+        return self._encoder(x)
 
     def transform(self, inputs):
         """Mean latent code q(z|x).mean (vae.py:105-112)."""
@@ -47,6 +58,30 @@ class VAE(_EngineBacked):
             comp = torch.multinomial(torch.softmax(logits, 0), num_samples, replacement=True, generator=self._noise_gen()).to(mu.device)
             return mu[comp] + sg[comp] * eps
         return eps
+
+
+class _Prior:
+    """The prior object `VAE.prior()` returns: `sample(n)` and `log_prob(z)` of N(0, I) or of the learned mixture."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def sample(self, n=1):
+        return self._m.generate_samples(int(n))
+
+    def log_prob(self, z):
+        import torch
+        eng = self._m.engine()
+        z = torch.as_tensor(z).to(eng.device, torch.float32).reshape(-1, eng.latent_size).contiguous()
+        mu, sg = eng.prior_table()                              # [K, Z] (K = 1: zeros / ones)
+        comps = []
+        for k in range(mu.shape[0]):                            # log N(z; loc_k, s_k) through the library's kernel
+            d = base.MultivariateNormalDiag(eng, mu[k:k + 1].expand(z.shape[0], -1).contiguous(), sg[k:k + 1].expand(z.shape[0], -1).contiguous())
+            comps.append(d.log_prob(z))
+        lp = torch.stack(comps, 1)
+        if self._m.mix_components > 1:                          # MixtureSameFamily.log_prob: logsumexp over components (vae.py:240-244)
+            lp = lp + torch.log_softmax(eng.parameters()["mixture_logits"], 0)[None]
+        return torch.logsumexp(lp, 1)
 
 
 class TrainableVAE(VAE):

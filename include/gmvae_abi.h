@@ -157,6 +157,26 @@ GMVAE_API int gmvae_encode(gmvae_handle* h, const uint8_t* x_u8, int batch, cons
 GMVAE_API int gmvae_decode(gmvae_handle* h, const float* z, int n, float* x_mean, void* stream);
 GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* stream);
 
+/* The callable distribution layer: Conditional{Normal,Bernoulli,Categorical}.condition(tensor_list) (base.py:63-72, 130-135,
+ * 193-198) = concat(inputs) -> MLP -> distribution parameters, on caller tensors (device float arrays, row-major):
+ *   GMVAE_COND_DECODER   in1 = z [n,Z]                    -> out_a = Bernoulli logits [n, data_size] (MLP(z) + bias_init)
+ *   GMVAE_COND_ENCODER   in1 = x [n,D] (in2 = y [n,K] for the GMVAE's encoder_gmm) -> out_a = mu, out_b = sigma [n,Z]
+ *   GMVAE_COND_ENCODER_Y in1 = x [n,D]                    -> out_a = logits of q(y|x) [n,K]
+ *   GMVAE_COND_PRIOR_GMM in1 = y [n,K]                    -> out_a = mu, out_b = sigma [n,Z]
+ * with sigma = max(softplus(raw + raw_sigma_bias), sigma_min) (base.py:69-70).  The model accessors decoder(z), encoder(x),
+ * encoder_y(x), encoder_gmm(x,y), prior_gmm(y) (gmvae.py:49-107, vae.py:41-78) are these.
+ * gmvae_dist_*: sample / log_prob / mean of the distributions those classes return (base.py:75-83, 138-146, 201-209):
+ * MultivariateNormalDiag(loc, scale_diag), Independent(Bernoulli(logits), 1), RelaxedOneHotCategorical(T, logits).  Noise is
+ * passed in (eps ~ N(0,1), u ~ U(0,1)); log_prob outputs are float[n]. */
+enum { GMVAE_COND_DECODER = 0, GMVAE_COND_ENCODER = 1, GMVAE_COND_ENCODER_Y = 2, GMVAE_COND_PRIOR_GMM = 3 };
+GMVAE_API int gmvae_condition(gmvae_handle* h, int which, const float* in1, const float* in2, int n, float* out_a, float* out_b,
+                    void* stream);
+GMVAE_API int gmvae_dist_normal_sample(const float* mu, const float* sigma, const float* eps, int64_t n, float* out, void* stream);
+GMVAE_API int gmvae_dist_normal_log_prob(const float* mu, const float* sigma, const float* z, int n, int d, float* out, void* stream);
+GMVAE_API int gmvae_dist_bernoulli_log_prob(const float* logits, const float* x, int n, int d, float* out, void* stream);
+GMVAE_API int gmvae_dist_bernoulli_mean(const float* logits, int64_t n, float* out, void* stream);
+GMVAE_API int gmvae_dist_relaxed_sample(const float* logits, const float* u, int n, int k, float temperature, float* out, void* stream);
+
 /* Input pipeline on the device = runners.create_dataset._preprocess (runners.py:44-47):
  *     image = cast(image, float32) / 255. ;  image = image < random.uniform(shape(image))
  * (dynamic, inverted binarisation: a pixel is 1 with probability 1 - intensity).
@@ -169,6 +189,11 @@ GMVAE_API int gmvae_prior_table(gmvae_handle* h, float* mu, float* sigma, void* 
  *   x_u8        [batch, data_size] bytes in {0,1}: what gmvae_forward_backward / gmvae_train_step take */
 GMVAE_API int gmvae_binarize(gmvae_handle* h, const uint8_t* intensities, int64_t n_rows, const int64_t* row_index,
                    int batch, uint64_t draw, uint8_t* x_u8, void* stream);
+
+/* Bit-packed binary images: packed [batch, ceil(data_size/8)] bytes, pixel 8j+k of a row in bit (7-k) of byte j
+ * (numpy.packbits order) -> x_u8 [batch, data_size] bytes in {0,1}.  The inputs of this path are binary (runners.py:44-47), so a
+ * host batch crosses PCIe as 98 bytes per image instead of 784. */
+GMVAE_API int gmvae_unpack_bits(gmvae_handle* h, const uint8_t* packed, int batch, uint8_t* x_u8, void* stream);
 
 /* Kernel-level test hook: C[M,N] = A[M,K] * B[K,N] through the same GEMM kernels the step
  * uses (impl 0 = fp32 SIMT, 1 = tcgen05 bf16).  A, B, C are device float arrays, row-major;
@@ -193,7 +218,8 @@ GMVAE_API int gmvae_debug_chain_jobs(gmvae_handle* h, int* out, int cap_jobs);
 /* Per-launch profile: with profiling on, a CUDA event is recorded after every launch of the
  * (eager) step; read() returns the summed device time and launch count per kernel class:
  * 0 tcgen05 GEMM fwd/dgrad, 1 tcgen05 GEMM wgrad, 2 SIMT GEMM, 3 distribution heads,
- * 4 bias gradients, 5 Adam + bf16 operand refresh, 6 misc (convert, noise, finalize). */
+ * 4 bias gradients, 5 Adam + bf16 operand refresh, 6 misc (convert, noise, finalize), 7 the gradient exchange
+ * (all-reduce; in-stream, so its interval is the exposed communication time).  n_classes >= 8. */
 GMVAE_API int gmvae_profile_enable(gmvae_handle* h, int on);
 GMVAE_API int gmvae_profile_read(gmvae_handle* h, double* ms_by_class, int64_t* launches_by_class, int n_classes);
 

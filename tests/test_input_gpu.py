@@ -93,3 +93,16 @@ def test_binarized_batch_feeds_the_step():
     loss = eng.train_step(x).cpu()
     assert torch.isfinite(loss).all() and loss[0] > 0
     eng.close()
+
+
+def test_unpack_bits_matches_numpy():
+    """gmvae_unpack_bits against numpy.unpackbits, D = 784 (aligned 8-byte stores) and a ragged D (tail bits, byte path)."""
+    import numpy as np
+    import gmvae_b200
+    for D, B in ((784, 257), (203, 33)):
+        eng = gmvae_b200.Engine("vae", data_size=D, latent_size=8, hidden_sizes=[16], mixture_components=1, max_batch=B, seed=1)
+        x = (np.random.default_rng(D).random((B, D)) < 0.4).astype(np.uint8)
+        packed = torch.from_numpy(np.packbits(x, axis=1)).cuda()
+        out = eng.unpack_bits(packed)
+        assert (out.cpu().numpy() == x).all()
+        eng.close()
