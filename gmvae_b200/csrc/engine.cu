@@ -133,6 +133,7 @@ enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8
        DBG_ROW_JOBS = 8192 /* force the distribution heads to run as row jobs of the chained kernel (the whole forward + backward
                               pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
                               vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
+       DBG_NO_PAIR = 65536 /* run the one-launch plan on single CTAs (tcgen05 cta_group::1, 128 x 256 tiles) instead of CTA pairs */,
        DBG_RELU_BITS = 2048 /* 1-bit ReLU masks between the chained forward and backward jobs: measured 1 % slower than
                                reading the bf16 activation through TMA, kept as an experiment */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
@@ -196,6 +197,8 @@ struct gmvae_handle {
   std::vector<int> chain_jobdesc;                  // 8 ints per job of that launch: kind, M, N, k-blocks, tiles, splits, block_n, ndeps
   bool chain_flush_after = false;
   bool row_jobs = false;                          // this step: distribution heads run as row jobs of the chained kernel
+  int wide_bn = 0;                                // tile width of jobs with more than 128 output columns (0: 256); GMVAE_CHAIN_BN
+  bool chain_pair = false;                        // this step: the chained kernel runs on CTA pairs (cta_group::2, 256-row tiles)
   // a y head to be fused into the epilogue of the next thin fp32 GEMM job (set by the step driver, consumed by chain_add)
   struct FuseReq { int kind = 0; unsigned char prm[tc::CHAIN_EPI2_BYTES]; std::vector<std::pair<const void*, size_t>> writes; bool consumed = false; };
   FuseReq fuse_next;
@@ -339,7 +342,7 @@ static int plan(gmvae_handle* h) {
     if (c.model == GMVAE_MODEL_GMVAE) { plan_shadows(h, h->encoder_y); plan_shadows(h, h->prior_gmm); }
   }
   plan_buf(h, "infer.acc", ACC_SLOTS * 4);
-  h->chain_counter_cap = 64 * (int)((Bfull + 127) / 128 + 1);
+  h->chain_counter_cap = 64 * (int)((Bfull + 127) / 128 + 2);
   plan_buf(h, "chain.counters", (size_t)h->chain_counter_cap * 4);
   return 0;
 }
@@ -417,8 +420,8 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   static bool attr_set_by_dev[64] = {};                      // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_by_dev[tc::current_device()];
   if (!attr_set) {
-    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
-    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
     attr_set = true;
   }
   h->chain.counters = h->chain_counters;
@@ -434,6 +437,27 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
     }
   }
   h->chain_launch_idx++;
+  if (h->chain_pair) {
+    // CTA pairs: clusters of 2 (the two SMs of a TPC); chain_tiles counts pair tiles.  Every cluster must be resident at once
+    // (the row-block waits assume it), so the grid is capped by what the device can co-schedule.
+    static int max_clusters_by_dev[64] = {};
+    int& max_clusters = max_clusters_by_dev[tc::current_device()];
+    if (max_clusters == 0) {
+      GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(tc::num_sms() & ~1); qc.blockDim = dim3(tc::NUM_THREADS2); qc.dynamicSmemBytes = tc::CHAIN_SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      GM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, tc::gemm_chain_kernel<tc::ChainParams, true>, &qc));
+      GM_REQUIRE(n >= 1, "the device cannot co-schedule a CTA pair of the chained kernel");
+      max_clusters = n;
+    }
+    const int pairs = std::max(1, std::min(std::min(h->chain_tiles, tc::num_sms() / 2), max_clusters));
+    GM_CHECK_CUDA(launch_k_cluster(tc::gemm_chain_kernel<tc::ChainParams, true>, dim3(2 * pairs), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, 2,
+                           h->chain));
+  } else {
   const int grid = std::min(h->chain_tiles, tc::num_sms());
   if (h->chain.njobs <= tc::CHAIN_SMALL_JOBS && h->chain.nmaps <= tc::CHAIN_SMALL_MAPS) {
     static tc::ChainParamsSmall small;                      // the launch copies it
@@ -441,9 +465,10 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
     small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta; small.jobstat = h->chain.jobstat;
     memcpy(small.maps, h->chain.maps, sizeof(CUtensorMap) * h->chain.nmaps);
     memcpy(small.jobs, h->chain.jobs, sizeof(tc::ChainJob) * h->chain.njobs);
-    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall, false>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
   } else {
-    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParams>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParams, false>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+  }
   }
   h->chain.njobs = 0; h->chain.nmaps = 0; h->chain_tiles = 0; h->chain_writers.clear();
   h->launches++;
@@ -485,7 +510,9 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
                      int M, int N, int block_n, bool a_mn, bool b_mn, int split_k, const Epi& epi, cudaStream_t st) {
   static_assert(tc::epi_kind<Epi>::value != tc::EK_NONE, "epilogue not supported by the chained kernel");
   static_assert(sizeof(Epi) <= tc::CHAIN_EPI_BYTES, "epilogue parameters do not fit the job record");
+  const bool pair = h->chain_pair;
   const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M, tiles_n = (N + block_n - 1) / block_n;
+  const int tiles_m_walk = pair ? (tiles_m + 1) / 2 : tiles_m;          // pair mode: tiles of 256 rows, one row block per CTA of the pair
   // ---- dependencies
   const void* reads[4] = {A1.ptr, A2 ? A2->ptr : nullptr, a_mn ? (const void*)B1.ptr : nullptr, epi.read_ptr()};
   tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0, epi_dep = -1;
@@ -522,12 +549,14 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
     if (mn) return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.rows, (uint64_t)o.k, (uint64_t)o.ld, 64, tc::BLOCK_K);
     return tc::make_tmap_bf16(m, o.ptr, (uint64_t)o.k, (uint64_t)o.rows, (uint64_t)o.ld, tc::BLOCK_K, (uint32_t)box_rows);
   };
+  const int b_box_rows = pair ? block_n / 2 : block_n;                 // K-major B: a CTA of a pair loads half of the tile's rows
+  GM_REQUIRE(!pair || block_n % 16 == 0, "pair tiles need a tile width that is a multiple of 16");
   GM_TRY(mk(&J.a1, A1, a_mn, tc::BLOCK_M));
-  GM_TRY(mk(&J.b1, B1, b_mn, block_n));
+  GM_TRY(mk(&J.b1, B1, b_mn, b_box_rows));
   J.kb1 = (A1.k + tc::BLOCK_K - 1) / tc::BLOCK_K; J.kb2 = 0;
   if (A2 && B2) {
     GM_TRY(mk(&J.a2, *A2, a_mn, tc::BLOCK_M));
-    GM_TRY(mk(&J.b2, *B2, b_mn, block_n));
+    GM_TRY(mk(&J.b2, *B2, b_mn, b_box_rows));
     J.kb2 = (A2->k + tc::BLOCK_K - 1) / tc::BLOCK_K;
   } else {
     J.a2 = J.a1; J.b2 = J.b1;
@@ -538,7 +567,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   split_k = (kb_total + per - 1) / per;
   J.M = M; J.N = N; J.kb_per_split = per; J.num_splits = split_k;
   J.block_n = block_n; J.a_mn = a_mn ? 1 : 0; J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
-  J.tiles_n = tiles_n; J.tiles_mn = tiles_m * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
+  J.tiles_n = tiles_n; J.tiles_mn = tiles_m_walk * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
   J.ndeps = ndeps; J.epi_dep = epi_dep;
   J.rot = (tiles_n > 1 && N % block_n != 0 && !a_mn) ? 1 : 0;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
@@ -546,8 +575,9 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   writer_range(epi, M, lo, hi);
   J.sig_base = -1;
   if (lo) {
-    if (h->chain_counter_next + tiles_m <= h->chain_counter_cap) {
-      J.sig_base = h->chain_counter_next; h->chain_counter_next += tiles_m;
+    const int ncount = pair ? 2 * tiles_m_walk : tiles_m;               // (a pair's phantom half signals a counter nobody waits for)
+    if (h->chain_counter_next + ncount <= h->chain_counter_cap) {
+      J.sig_base = h->chain_counter_next; h->chain_counter_next += ncount;
     } else {
       h->chain_flush_after = true;     // out of counters: later readers are ordered by the kernel boundary
     }
@@ -608,7 +638,8 @@ static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::i
   tc::ChainJob& J = h->chain.jobs[h->chain.njobs];
   memset(&J, 0, sizeof(J));
   J.M = M; J.N = 0; J.kind = kind; J.num_splits = 1;
-  J.tiles_n = sub; J.tiles_mn = tiles_m * sub; J.total_tiles = tiles_m * sub; J.tile_base = h->chain_tiles;   // sub tiles per 128-row block
+  // row tiles are dealt to single CTAs also in pair mode, where chain_tiles counts pair tiles
+  J.tiles_n = sub; J.tiles_mn = tiles_m * sub; J.total_tiles = tiles_m * sub; J.tile_base = h->chain_pair ? 2 * h->chain_tiles : h->chain_tiles;
   J.ndeps = ndeps; J.epi_dep = -1;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
   J.sig_base = -1;
@@ -620,7 +651,7 @@ static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::i
   for (const auto& w : writes)
     if (w.first) h->chain_writers.push_back({reinterpret_cast<const char*>(w.first), reinterpret_cast<const char*>(w.first) + w.second, h->chain.njobs});
   memcpy(J.epi, &prm, sizeof(P));
-  h->chain_tiles += J.total_tiles;
+  h->chain_tiles += h->chain_pair ? (J.total_tiles + 1) / 2 : J.total_tiles;
   h->chain.njobs++;
   if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
   return 0;
@@ -635,7 +666,8 @@ static int tc_dispatch_kk(gmvae_handle* h, const tc::Operand& A, const tc::Opera
     if (h->chain_on && chain_io(epi).ok) {
       // outputs staged for TMA stores use tiles that are whole 32-column groups; MN-major B comes in 64-column slabs
       const bool f32 = tc::epi_kind<Epi>::value == tc::EK_STORE_F32;
-      const int bn = (!B_MN && f32 && N <= 16) ? 16 : (!B_MN && f32 && N <= 32) ? 32 : N <= 64 ? 64 : (N <= 128 || (h->debug_flags & DBG_BN128)) ? 128 : 256;
+      int bn = (!B_MN && f32 && N <= 16) ? 16 : (!B_MN && f32 && N <= 32) ? 32 : N <= 64 ? 64 : (N <= 128 || (h->debug_flags & DBG_BN128)) ? 128 : 256;
+      if (bn == 256 && h->wide_bn > 0 && N > h->wide_bn) bn = h->wide_bn;       // tile width of the wide layers (GMVAE_CHAIN_BN)
       return chain_add(h, A, B, A2, B2, M, N, bn, false, B_MN, 1, epi, st);
     }
   }
@@ -715,11 +747,12 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
     if (ok) {
       tc::Operand a{A, lda, kpad(L.in, lda), M}, b{dY, ldy, kpad(L.out, ldy), M};
       const int bn = L.out <= 64 ? 64 : (L.out <= 128 || (h->debug_flags & DBG_BN128)) ? 128 : 256;
-      const int tiles = ((L.in + 127) / 128) * ((L.out + bn - 1) / bn);
+      const bool pair = h->chain_on && h->chain_pair;
+      const int tiles = pair ? ((L.in + 255) / 256) * ((L.out + bn - 1) / bn) : ((L.in + 127) / 128) * ((L.out + bn - 1) / bn);
       const int kb = (M + tc::BLOCK_K - 1) / tc::BLOCK_K;
-      // one wave of persistent CTAs: split the batch so that tiles * split ~ number of SMs,
+      // one wave of persistent CTAs (CTA pairs): split the batch so that tiles * split ~ number of SMs (pairs),
       // keeping at least 4 k-blocks (256 samples) per split
-      int split = std::max(1, std::min(std::max(1, kb / 4), tc::num_sms() / tiles));
+      int split = std::max(1, std::min(std::max(1, kb / 4), (pair ? tc::num_sms() / 2 : tc::num_sms()) / tiles));
       if (h->chain_on) return chain_add(h, a, b, nullptr, nullptr, L.in, L.out, bn, true, true, split, epi, st);
       GM_TRY(chain_flush(h, st));
       int r = bn == 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
@@ -1000,10 +1033,12 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   // Heads as row jobs (one launch for the whole pass) pay off once there are enough 128-row blocks to keep the SMs busy
   // across the dependent thin jobs; below that the heads run as separate kernels between chained launches.
   h->row_jobs = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && (B >= 32 * tc::BLOCK_M || (h->debug_flags & DBG_ROW_JOBS));
+  // CTA pairs (256-row tiles) where the one-launch plan runs: large batches, every SM available
+  h->chain_pair = h->row_jobs && !(h->debug_flags & DBG_NO_PAIR) && !(h->comm && h->world > 1 && h->overlap_comm) && tc::g_reserved_sms == 0;
   if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
   int r = forward_backward_body<A>(h, x_u8, B, Bg, eps_in, u_in, st);
   if (r == 0) r = chain_flush(h, st);
-  h->chain_on = false; h->chain.njobs = 0; h->chain.nmaps = 0;
+  h->chain_on = false; h->chain_pair = false; h->chain.njobs = 0; h->chain.nmaps = 0;
   return r;
 }
 
@@ -1441,6 +1476,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
   h->debug_flags = dbg ? atoi(dbg) : 0;
   g_use_pdl = !(h->debug_flags & DBG_NO_PDL);
+  if (const char* bnv = getenv("GMVAE_CHAIN_BN")) { const int v = atoi(bnv); if (v == 128 || v == 192) h->wide_bn = v; }
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
   DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull; s0.adam_blocks = 0; s0.pad = 0;

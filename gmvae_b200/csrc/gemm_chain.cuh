@@ -52,6 +52,10 @@ constexpr int CHAIN_MAX_MAPS = 112;    // tensor maps of all jobs (operands, TMA
 constexpr int CHAIN_MAX_DEPS = 4;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
+// CTA-pair mode (cta_group::2, see gemm_tc.cuh): a stage holds this CTA's 128 rows of A and HALF of the B tile's columns
+constexpr int CHAIN_STAGES_PAIR = 6;
+constexpr int CHAIN_STAGE_BYTES_PAIR = A_STAGE_BYTES + 128 * BLOCK_K * 2;   // 32 KB
+static_assert(CHAIN_STAGES_PAIR * CHAIN_STAGE_BYTES_PAIR == CHAIN_STAGES * CHAIN_STAGE_BYTES, "both modes use the same ring area");
 constexpr int CHAIN_EPI_BYTES = 128;
 constexpr int CHAIN_EPI2_BYTES = 64;
 constexpr int CHAIN_PATCH_BYTES = 2048;   // per epilogue warp: 32 rows x 64 B, the box of one TMA store (SWIZZLE_64B like the tensor map)
@@ -131,13 +135,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int mn
 // is rotated by the row block: a job whose last n-tile is ragged (784 = 3 x 256 + 16) has cheap and expensive tiles, and since
 // the CTAs walk the tile sequence with a stride (148) that is a multiple of tiles_n, every CTA would otherwise see one n-tile
 // index only -- a quarter of the CTAs all the cheap tiles, the rest all the expensive ones.
-__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int& z, int& mb, int& n0) {
+// PAIR: the job's tile space is in PAIR tiles of 256 rows (J.tiles_mn = ceil(row blocks / 2) * tiles_n); CTA `rank` of the pair owns
+// row block 2 * pm + rank (possibly beyond M: a phantom half whose loads read zeros and whose stores are clipped).
+template <bool PAIR>
+__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int rank, int& z, int& mb, int& n0) {
   z = l / J.tiles_mn;
   const int mn = l - z * J.tiles_mn;
-  mb = mn / J.tiles_n;
-  int nt = mn - mb * J.tiles_n;
-  if (J.rot) { nt += mb % J.tiles_n; if (nt >= J.tiles_n) nt -= J.tiles_n; }
+  const int pm = mn / J.tiles_n;
+  int nt = mn - pm * J.tiles_n;
+  if (J.rot) { nt += pm % J.tiles_n; if (nt >= J.tiles_n) nt -= J.tiles_n; }
   n0 = nt * J.block_n;
+  mb = PAIR ? 2 * pm + rank : pm;
 }
 
 struct ChainShared {
@@ -325,16 +333,19 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
 // LSU (measured before: ~16 B/clk/SM, the limiter of the whole step), rows/columns beyond M/N are
 // clipped by the tensor map, and no st.global is issued by the epilogue warps at all.  The ReLU mask
 // source of the backward pass arrives the same way (TMA load of the box into the patch).
-template <class Epi, int KIND>
+template <class Epi, int KIND, bool PAIR>
 __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUtensorMap* maps, int* counters, const ChainShared& S, int& it,
                                                    uint32_t& op_phase, int warp, int lane, long long* trace, int jidx,
                                                    unsigned long long* jobstat = nullptr) {
   constexpr int CW = 16;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
-  const int G = gridDim.x;
-  const int first = (((int)blockIdx.x - J.tile_base) % G + G) % G;
+  // GEMM tiles are dealt round-robin to the CTAs -- in pair mode to the CTA pairs, both CTAs of a pair walking the same pair tiles
+  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int cidx = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+  const int first = ((cidx - J.tile_base) % G + G) % G;
   if (first >= J.total_tiles) return;
-  const int M = J.M, N = J.N, BN = J.block_n, tiles_n = J.tiles_n, tiles_mn = J.tiles_mn;
+  const int M = J.M, N = J.N, BN = J.block_n;
   const int nchunk = BN / CW;
   const int e = warp - 2, quad = warp & 3, slot = e >> 2;
   const int et = (int)threadIdx.x - 64;
@@ -358,7 +369,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
   };
   for (int l = first; l < J.total_tiles; l += G, ++it) {
     int z, mb, n0;
-    chain_tile(J, l, z, mb, n0);
+    chain_tile<PAIR>(J, l, rank, z, mb, n0);
     const int m0 = mb * BLOCK_M;
     const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
     const int mrow0 = m0 + quad * 32;
@@ -387,7 +398,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     unsigned long long js_t0 = 0, js_t1 = 0;
     // The epilogue's own operand (ReLU mask source) is fetched ahead of the accumulator, i.e. possibly
     // before the TMA producer has seen this tile's dependencies: the warp checks the operand's producer itself.
-    if (J.epi_dep >= 0) {
+    if (J.epi_dep >= 0 && m0 < M) {                         // (a pair's phantom half has no producer to wait for)
       if (lane == 0) { wait_counter(counters + J.deps[J.epi_dep].base + mb, J.deps[J.epi_dep].target); fence_proxy_async_global(); }
       __syncwarp();
     }
@@ -625,7 +636,8 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     }
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(&S.tmem_empty_bar[as]);
+      if (PAIR) mbar_arrive_leader(&S.tmem_empty_bar[as]);   // the leader's MMA warp waits for the epilogue warps of both CTAs
+      else mbar_arrive(&S.tmem_empty_bar[as]);
       if (J.sig_base >= 0) {
         // rows stored by the bulk copies (async proxy) must be complete and visible before the row block is released
         if constexpr (KIND != EK_STORE_F32) { bulk_wait0(); fence_proxy_async_global(); }
@@ -844,9 +856,9 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
   }
 }
 
-template <class Params>
+template <class Params, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __grid_constant__ Params p) {
-  constexpr int STAGES = CHAIN_STAGES, STAGE_BYTES = CHAIN_STAGE_BYTES;
+  constexpr int STAGES = PAIR ? CHAIN_STAGES_PAIR : CHAIN_STAGES, STAGE_BYTES = PAIR ? CHAIN_STAGE_BYTES_PAIR : CHAIN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   if (smem - smem_raw + CHAIN_CARVE_BYTES > CHAIN_SMEM_BYTES) __trap();   // dynamic shared memory starts (at most 512 B off) a 1 KB boundary
@@ -862,20 +874,26 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   float* scs_all = sbias_all + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x, c = blockIdx.x;
-  long long* const trace = (p.trace && c == p.trace_cta) ? p.trace : nullptr;
+  // GEMM tiles: G walkers (CTAs, or CTA pairs), this one is number c; `rank` = this CTA's place in its pair
+  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x, c = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+  long long* const trace = (p.trace && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nmaps; ++i) tma_prefetch_desc(&p.maps[i]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&op_bar[s], 1);
     fence_barrier_init();
   } else if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) {
+    if (cluster_ctarank() != (uint32_t)rank) __trap();      // the pair must be the two CTAs of one cluster, leader = even block
+    cluster_sync_all();                                       // the peer's barriers exist before anything is signalled on them
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();
@@ -889,13 +907,20 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
       for (int j = 0; j < p.njobs; ++j) {
         const ChainJob& J = p.jobs[j];
         if (J.kind >= EK_ROWS_FIRST) continue;              // row jobs have no GEMM
-        const int tiles_n = J.tiles_n, tiles_mn = J.tiles_mn, BN = J.block_n, kb1 = J.kb1, kb_total = J.kb1 + J.kb2;
-        const uint32_t tx_bytes = (uint32_t)(A_STAGE_BYTES + BN * BLOCK_K * 2);
+        const int BN = J.block_n, kb1 = J.kb1, kb_total = J.kb1 + J.kb2;
+        // pair mode: this CTA loads its 128 rows of A and HALF of the B tile (K-major: BN/2 rows; MN-major: 64-column slabs)
+        const int bhalf = BN >> 1;
+        const int b_slabs = PAIR ? (bhalf + 63) / 64 : BN / 64;
+        const uint32_t b_bytes = PAIR ? (uint32_t)(J.b_mn ? b_slabs * (BLOCK_K * 128) : bhalf * BLOCK_K * 2) : (uint32_t)(BN * BLOCK_K * 2);
+        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * ((uint32_t)A_STAGE_BYTES + b_bytes);    // pair: both CTAs' loads land on the leader's barrier
         const int first = ((c - J.tile_base) % G + G) % G;
         for (int l = first; l < J.total_tiles; l += G, ++pit) {
           int z, mb, n0;
-          chain_tile(J, l, z, mb, n0);
+          chain_tile<PAIR>(J, l, rank, z, mb, n0);
           const int m0 = mb * BLOCK_M;
+          const bool real = J.a_mn || m0 < J.M;              // K-major A: rows m0.. exist (a pair's second half may lie beyond M)
+          const int n_eff = min(BN, (J.N - n0 + 15) & ~15);
+          const int nb = PAIR ? n0 + rank * (n_eff >> 1) : n0;  // first B column this CTA loads
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
           const bool tr = trace && pit < 64;
           if (tr) trace[16 * pit + 0] = clock64();
@@ -906,7 +931,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
               const ChainDep& D = J.deps[d];
               if (D.seg2) continue;
               if (!D.by_k) {
-                wait_counter(p.counters + D.base + mb, D.target);
+                if (real) wait_counter(p.counters + D.base + mb, D.target);
               } else {
                 const int lo = (kb_begin * BLOCK_K) / BLOCK_M, hi = min(D.nblocks - 1, (kb_end * BLOCK_K - 1) / BLOCK_M);
                 for (int b = lo; b <= hi; ++b) wait_counter(p.counters + D.base + b, D.target);
@@ -921,7 +946,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
               // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
               bool any = false;
               for (int d = 0; d < J.ndeps; ++d)
-                if (J.deps[d].seg2) { wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
+                if (J.deps[d].seg2) { if (real) wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
               if (any) fence_proxy_async_global();
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -931,17 +956,20 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
             const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+              if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1); else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+            };
             if (J.a_mn) {
 #pragma unroll
-              for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+              for (int i = 0; i < BLOCK_M / 64; ++i) ld(ta, sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
             } else {
-              tma_load_2d(ta, &full_bar[stage], sa, k_elem, m0);
+              ld(ta, sa, k_elem, m0);
             }
             if (J.b_mn) {
-              for (int i = 0; i < BN / 64; ++i) tma_load_2d(tb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
+              for (int i = 0; i < b_slabs; ++i) ld(tb, sb + i * (BLOCK_K * 128), nb + i * 64, k_elem);
             } else {
-              tma_load_2d(tb, &full_bar[stage], sb, k_elem, n0);
+              ld(tb, sb, k_elem, nb);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -951,22 +979,22 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
+      // ===== MMA issuer (single thread; in pair mode the leader CTA's, for both CTAs) =====
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int j = 0; j < p.njobs; ++j) {
+      for (int j = 0; (!PAIR || rank == 0) && j < p.njobs; ++j) {
         const ChainJob& J = p.jobs[j];
         if (J.kind >= EK_ROWS_FIRST) continue;
-        const int tiles_mn = J.tiles_mn, kb_total = J.kb1 + J.kb2;
+        const int kb_total = J.kb1 + J.kb2;
         const int a_mn = J.a_mn, b_mn = J.b_mn;
         const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-                                ((uint32_t)(BLOCK_M >> 4) << 24);
+                                ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
         const uint64_t a_step = a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         const uint64_t b_step = b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         const int first = ((c - J.tile_base) % G + G) % G;
         for (int l = first; l < J.total_tiles; l += G, ++it) {
           int z, mb_unused, n0;
-          chain_tile(J, l, z, mb_unused, n0);
+          chain_tile<PAIR>(J, l, 0, z, mb_unused, n0);
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
           const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
           // a ragged last n-tile runs a narrower MMA (N multiple of 16): the zero-filled columns are not multiplied
@@ -989,12 +1017,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
             const uint64_t bdesc = make_smem_desc_rt(sa + A_STAGE_BYTES, b_mn);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma_bf16(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              if (PAIR) umma_bf16_pair(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              else umma_bf16(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full_bar[as]);
+          if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
           if (tr) trace[16 * it + 5] = clock64();
           if (p.jobstat) { atomicAdd(p.jobstat + 8 * j + 3, gtimer() - js_t1); atomicAdd(p.jobstat + 8 * j + 7, js_t1 - js_t0); }
         }
@@ -1008,11 +1037,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
 #ifndef GMVAE_NO_ROWS
         case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
         case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
@@ -1026,9 +1055,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   if (warp >= 2 && lane == 0) bulk_wait0();     // outstanding bulk stores read this CTA's shared memory
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // no CTA of a pair leaves (or frees tensor memory) while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
