@@ -163,6 +163,8 @@ struct gmvae_handle {
   ShadowEntry* shadow_dev = nullptr; int shadow_tiles = 0;
   DeviceState* state = nullptr;
   uint64_t seed_host = 0;                // host copy of state->seed (it changes only through gmvae_set_seed)
+  bool grads_clean = false;              // the gradient buffer and the loss accumulators are all zero (the training step's Adam clears them)
+  bool graph_has_memset = true;          // the captured step starts with its own clearing memset
   uint64_t draws = 0;                    // noise draws made outside training steps (mixed into the Philox key, kernels.cuh fill_noise_body)
   bool in_train_step = false;
   int64_t launches = 0;
@@ -1052,7 +1054,10 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   const bool gm = c.model == GMVAE_MODEL_GMVAE;
   float* acc = h->grads + h->n_params;
   if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
-  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  // gradients accumulate (split-K weight gradients, column sums, loss terms): start from zeros -- left behind by the previous
+  // training step's Adam kernel, or cleared here
+  if (!h->grads_clean) GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  h->grads_clean = false;
   h->reduced_upto = 0;
 
   const float* eps = eps_in; const float* u = u_in;
@@ -1269,7 +1274,8 @@ static int forward_backward_marginal(gmvae_handle* h, const uint8_t* x_u8, int B
   const float inv_bg = 1.f / (float)Bg;
   float* acc = h->grads + h->n_params;
   if (h->profiling) GM_TRY(profile_mark(h, st, PC_START));
-  GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  if (!h->grads_clean) GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, st));
+  h->grads_clean = false;
   h->reduced_upto = 0;
   double* rec = h->buf<double>("rec"); float* klrow = h->buf<float>("klrow");
   float* tab = h->buf<float>("tab"); float* dtab = h->buf<float>("dtab");
@@ -1479,7 +1485,7 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   if (const char* bnv = getenv("GMVAE_CHAIN_BN")) { const int v = atoi(bnv); if (v == 128 || v == 192) h->wide_bn = v; }
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));
-  DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull; s0.adam_blocks = 0; s0.pad = 0;
+  DeviceState s0; s0.step = 0; s0.seed = 0x243F6A8885A308D3ull; s0.adam_blocks = 0; s0.pad = 0; s0.beta1_power = 1.0; s0.beta2_power = 1.0;
   h->seed_host = s0.seed;
   GM_CHECK_CUDA(cudaMemcpy(h->state, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   *out = h;
@@ -1576,24 +1582,26 @@ int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
 }
 
 // Adam (+ optionally the loss-term finalisation, folded into the same launch by gmvae_train_step)
-static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st) {
+static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st, bool zero_grads) {
   const gmvae_config& c = h->cfg;
   int64_t n = h->n_params;
   // after a cross-stream join (data-parallel all-reduce) the kernel is launched with a full dependency
   const bool pdl = !(h->comm && h->world > 1 && (h->debug_flags & DBG_COMM_OVERLAP));
-  // one launch: parameter update, the bf16 operand copies of the weight matrices, global_step += 1
-  GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n / 4 + 255) / 256 + 1)), dim3(256), 0, st, pdl, h->params, (const float*)h->grads,
+  // one launch: parameter update, the bf16 operand copies of the weight matrices, global_step += 1, (training step) gradients cleared
+  const int64_t per_block = (int64_t)ADAM_THREADS * 4 * ADAM_VEC;
+  GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n + per_block - 1) / per_block)), dim3(ADAM_THREADS), 0, st, pdl, h->params, h->grads,
                          h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, h->state,
-                         (const float*)(h->grads + h->n_params), loss_terms, (const ShadowEntry*)h->shadow_dev,
-                         h->bf16_mode() ? (int)h->shadow_host.size() : 0));
+                         h->grads + h->n_params, loss_terms, (const ShadowEntry*)h->shadow_dev,
+                         h->bf16_mode() ? (int)h->shadow_host.size() : 0, zero_grads ? 1 : 0));
   GM_LAUNCHED(h, st, PC_ADAM);
+  h->grads_clean = zero_grads;
   return 0;
 }
 
 int gmvae_adam_step(gmvae_handle* h, void* stream) {
   DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
-  return adam_step_impl(h, nullptr, (cudaStream_t)stream);
+  return adam_step_impl(h, nullptr, (cudaStream_t)stream, false);     // stand-alone: the gradients stay readable
 }
 
 int gmvae_get_step(gmvae_handle* h, int64_t* step, void* stream) {
@@ -1609,7 +1617,9 @@ int gmvae_set_step(gmvae_handle* h, int64_t step, void* stream) {
   DeviceGuard dev_guard(h);
   GM_REQUIRE(h, "null argument");
   long long v = step;
+  const double pw[2] = {pow((double)h->cfg.beta1, (double)step), pow((double)h->cfg.beta2, (double)step)};   // the beta-power accumulators follow the step
   GM_CHECK_CUDA(cudaMemcpyAsync(&h->state->step, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  GM_CHECK_CUDA(cudaMemcpyAsync(&h->state->beta1_power, pw, sizeof(pw), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   GM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
@@ -1745,7 +1755,7 @@ int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global
   if (r == 0) r = gmvae_allreduce_grads(h, stream);
   h->overlap_comm = false;
   GM_TRY(r);
-  return adam_step_impl(h, loss_terms, (cudaStream_t)stream);
+  return adam_step_impl(h, loss_terms, (cudaStream_t)stream, true);
 }
 
 int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,
@@ -1757,6 +1767,7 @@ int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, in
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
   // Warm every kernel once outside capture (function attributes, tensor-map cache, lazy module load).
   int saved = h->debug_flags; h->debug_flags &= ~DBG_SYNC_EACH;
+  h->graph_has_memset = !h->grads_clean;                     // the step clears the gradients itself only when they are not already zero
   GM_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   int r = gmvae_train_step(h, x_u8, batch, global_batch, eps, gumbel_u, loss_terms, stream);
   cudaGraph_t graph = nullptr;
@@ -1764,6 +1775,8 @@ int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, in
   h->debug_flags = saved;
   if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
   GM_CHECK_CUDA(e);
+  // nothing ran during capture: the buffer is in the state it was in before
+  h->grads_clean = !h->graph_has_memset;
   e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
   cudaGraphDestroy(graph);
   GM_CHECK_CUDA(e);
@@ -1772,7 +1785,12 @@ int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, in
 int gmvae_step_graph_launch(gmvae_handle* h, void* stream) {
   DeviceGuard dev_guard(h);
   GM_REQUIRE(h && h->graph_exec, "no captured graph");
+  // a graph captured without the clearing memset relies on the previous step's Adam kernel; after an eager forward_backward in
+  // between the gradients are cleared here
+  if (!h->graph_has_memset && !h->grads_clean)
+    GM_CHECK_CUDA(cudaMemsetAsync(h->grads, 0, (size_t)(h->n_params + ACC_SLOTS) * 4, (cudaStream_t)stream));
   GM_CHECK_CUDA(cudaGraphLaunch(h->graph_exec, (cudaStream_t)stream));
+  h->grads_clean = true;
   return 0;
 }
 

@@ -19,8 +19,9 @@ struct ShadowEntry {
 struct DeviceState {           // owned by the handle, lives on the device
   long long step;              // global_step (runners.py:171)
   unsigned long long seed;
-  unsigned int adam_blocks;    // blocks of the running Adam launch that have read `step` (the last one bumps it)
+  unsigned int adam_blocks;    // blocks of the running Adam launch that have read the state (the last one advances it)
   unsigned int pad;
+  double beta1_power, beta2_power;   // beta^step: tf.train.AdamOptimizer's non-trainable beta1_power / beta2_power accumulators
 };
 
 // ---- x: bool bytes -> GEMM operand type (vae.py:75, gmvae.py:86,104: tf.cast(x, float32)) ----
@@ -1071,74 +1072,96 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __res
 // ---- tf.train.AdamOptimizer (runners.py:181-183) ------------------------
 // lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // theta -= lr_t m / (sqrt(v) + eps).   t = step+1 read from the device; one flat pass.
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+// Also (training step only, `zero_grads`): the gradient buffer and the loss accumulators are cleared once read, so the next step
+// starts from zeros without a separate memset node.  8 elements per thread, every load issued before the block waits for lr_t.
+constexpr int ADAM_THREADS = 256, ADAM_VEC = 2;              // float4 groups per thread
+__global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float lr, float b1, float b2, float eps, DeviceState* st,
-                            const float* __restrict__ acc, float* __restrict__ loss_out,
-                            const ShadowEntry* __restrict__ shadows, int n_shadows) {
+                            float* __restrict__ acc, float* __restrict__ loss_out,
+                            const ShadowEntry* __restrict__ shadows, int n_shadows, int zero_grads) {
   griddep_wait();
   griddep_launch();
   __shared__ float lr_t_s;
   __shared__ int e0_s;
-  if (loss_out && blockIdx.x == 0 && threadIdx.x == 32) {   // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
-    float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
-    loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
+  if (blockIdx.x == 0 && threadIdx.x == 32) {
+    if (loss_out) {                                          // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
+      float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
+      loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
+    }
+    if (zero_grads)
+      for (int i = 0; i < ACC_SLOTS; ++i) acc[i] = 0.f;
   }
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x * 4;
+  const int64_t i0 = (int64_t)blockIdx.x * ADAM_THREADS * 4 * ADAM_VEC;
+  // operands first: the loads are in flight while thread 0 works out the step size
+  float4 pp[ADAM_VEC], gg[ADAM_VEC], mm[ADAM_VEC], vv[ADAM_VEC];
+  int64_t idx[ADAM_VEC];
+#pragma unroll
+  for (int u = 0; u < ADAM_VEC; ++u) {
+    idx[u] = i0 + ((int64_t)u * ADAM_THREADS + threadIdx.x) * 4;
+    if (idx[u] + 4 <= n) {
+      pp[u] = *reinterpret_cast<float4*>(p + idx[u]); gg[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+      mm[u] = *reinterpret_cast<float4*>(m + idx[u]); vv[u] = *reinterpret_cast<float4*>(v + idx[u]);
+    }
+  }
   if (threadIdx.x == 0) {
-    double t = (double)(st->step + 1);
-    lr_t_s = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
-    // global_step += 1 once every block of this launch has read it: the last block to get here does it
+    // lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t), t = step + 1, from the running powers (as TF keeps them)
+    const double b1t = st->beta1_power * (double)b1, b2t = st->beta2_power * (double)b2;
+    lr_t_s = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    // global_step += 1 and the powers advance once every block of this launch has read them: the last block to get here does it
     __threadfence();
-    if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) { st->adam_blocks = 0; st->step += 1; }
+    if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) { st->adam_blocks = 0; st->step += 1; st->beta1_power = b1t; st->beta2_power = b2t; }
   } else if (threadIdx.x == 64) {
     // the weight matrix the block's first element belongs to (entries are sorted by flat offset); the block's
-    // 1024 elements almost always lie in the same matrix, so the threads only step forward from here
+    // elements almost always lie in the same matrix, so the threads only step forward from here
     int lo = 0, hi = n_shadows;                             // first entry with off > i0
     while (lo < hi) { int mid = (lo + hi) >> 1; if (shadows[mid].off <= i0) lo = mid + 1; else hi = mid; }
     e0_s = lo - 1;
   }
   __syncthreads();
   const float lr_t = lr_t_s;
-  int64_t i = i0 + (int64_t)threadIdx.x * 4;
-  if (i >= n) return;
-  // tensors start on 16-byte boundaries, so a group of 4 never straddles two
   int e = e0_s;
-  while (e + 1 < n_shadows && shadows[e + 1].off <= i) ++e;
-  bf16* wb = nullptr; int cols = 0, ld_w = 0; int64_t rel = 0, lim = 0;
-  if (e >= 0) {
-    const ShadowEntry& E = shadows[e];
-    rel = i - E.off; lim = (int64_t)E.rows * E.cols;
-    if (rel < lim) { wb = E.w_bf16; cols = E.cols; ld_w = E.ld_w; }
-  }
-  if (i + 4 <= n) {
-    float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
-    float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
-    float* P = &pp.x; const float* G = &gg.x; float* Mm = &mm.x; float* V = &vv.x;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      Mm[j] = b1 * Mm[j] + (1.f - b1) * G[j];
-      V[j] = b2 * V[j] + (1.f - b2) * G[j] * G[j];
-      P[j] -= lr_t * Mm[j] / (sqrtf(V[j]) + eps);
+  for (int u = 0; u < ADAM_VEC; ++u) {
+    const int64_t i = idx[u];
+    if (i >= n) continue;
+    // tensors start on 16-byte boundaries, so a group of 4 never straddles two
+    while (e + 1 < n_shadows && shadows[e + 1].off <= i) ++e;
+    bf16* wb = nullptr; int cols = 0, ld_w = 0; int64_t rel = 0, lim = 0;
+    if (e >= 0) {
+      const ShadowEntry& E = shadows[e];
+      rel = i - E.off; lim = (int64_t)E.rows * E.cols;
+      if (rel < lim) { wb = E.w_bf16; cols = E.cols; ld_w = E.ld_w; }
     }
-    *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
-    if (wb) {                                               // bf16 GEMM operand copy [rows, ld_w] of the updated weights
-      if (cols == ld_w && rel + 4 <= lim) {
-        *reinterpret_cast<uint2*>(wb + rel) = make_uint2(pack_bf16x2(P[0], P[1]), pack_bf16x2(P[2], P[3]));
-      } else {
+    if (i + 4 <= n) {
+      float* P = &pp[u].x; const float* G = &gg[u].x; float* Mm = &mm[u].x; float* V = &vv[u].x;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t el = rel + j;
-          if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(P[j]);
+      for (int j = 0; j < 4; ++j) {
+        Mm[j] = b1 * Mm[j] + (1.f - b1) * G[j];
+        V[j] = b2 * V[j] + (1.f - b2) * G[j] * G[j];
+        P[j] -= lr_t * Mm[j] / (sqrtf(V[j]) + eps);
+      }
+      *reinterpret_cast<float4*>(p + i) = pp[u]; *reinterpret_cast<float4*>(m + i) = mm[u]; *reinterpret_cast<float4*>(v + i) = vv[u];
+      if (zero_grads) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wb) {                                               // bf16 GEMM operand copy [rows, ld_w] of the updated weights
+        if (cols == ld_w && rel + 4 <= lim) {
+          *reinterpret_cast<uint2*>(wb + rel) = make_uint2(pack_bf16x2(P[0], P[1]), pack_bf16x2(P[2], P[3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t el = rel + j;
+            if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(P[j]);
+          }
         }
       }
-    }
-  } else {
-    for (int64_t k = i; k < n; ++k) {
-      float mk = b1 * m[k] + (1.f - b1) * g[k];
-      float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
-      m[k] = mk; v[k] = vk;
-      p[k] -= lr_t * mk / (sqrtf(vk) + eps);
-      if (wb) { const int64_t el = rel + (k - i); if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(p[k]); }
+    } else {
+      for (int64_t k = i; k < n; ++k) {
+        float mk = b1 * m[k] + (1.f - b1) * g[k];
+        float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
+        m[k] = mk; v[k] = vk;
+        p[k] -= lr_t * mk / (sqrtf(vk) + eps);
+        if (zero_grads) g[k] = 0.f;
+        if (wb) { const int64_t el = rel + (k - i); if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(p[k]); }
+      }
     }
   }
 }

@@ -81,7 +81,17 @@ def test_factory_signatures_match_reference():
     assert m._prior_gmm.variable_names() == ["prior_gmm_fcnet/linear_0/w", "prior_gmm_fcnet/linear_0/b"]
     assert m._encoder_y.output_sizes == [8, 10] and m._encoder_gmm.output_sizes == [8, 16]
     v = gmvae_b200.create_vae(784, 8, mixture_components=10, fcnet_hidden_sizes=[32, 32])
-    assert isinstance(v, gmvae_b200.TrainableVAE) and v.prior() == "mixture"
+    assert isinstance(v, gmvae_b200.TrainableVAE) and v._prior == "mixture"
+    assert hasattr(v.prior(), "log_prob") and hasattr(v.prior(), "sample")          # vae.py:41-48: prior() returns a distribution
+    for acc in ("prior_gmm", "decoder", "encoder_y", "encoder_gmm"):                 # gmvae.py:49-107
+        assert callable(getattr(m, acc))
+    for acc in ("prior", "decoder", "encoder"):                                      # vae.py:41-78
+        assert callable(getattr(v, acc))
+    import gmvae_b200.base as base
+    for cls in (base.ConditionalNormal, base.ConditionalBernoulli, base.ConditionalCategorical):
+        assert callable(getattr(cls, "condition")) and callable(getattr(cls, "__call__"))
+    with pytest.raises(RuntimeError):                                                # not part of a model: no variables to run
+        base.ConditionalNormal(size=4, name="free").condition([torch.zeros(2, 3)])
     assert list(inspect.signature(v.run_model).parameters)[:2] == ["images", "targets"]
     assert list(inspect.signature(m.run_model).parameters)[:3] == ["images", "targets", "labels"]
     with pytest.raises(NotImplementedError):

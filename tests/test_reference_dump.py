@@ -92,12 +92,13 @@ def test_cuda_step_matches_reference_dump(path):
                             mixture_components=cfg["mixture_components"], precision="fp32", max_batch=cfg["batch_size"],
                             learning_rate=cfg["learning_rate"], init=False)
     eng.set_parameters(params)
-    t = eng.train_step(x, eps=eps, gumbel_u=u).cpu().tolist()
+    t = eng.forward_backward(x, eps=eps, gumbel_u=u).cpu().tolist()     # (train_step clears the gradient buffer once Adam has read it)
     for i, k in enumerate(("loss", "nll", "kl_div_z", "nent")):
         assert abs(t[i] - terms[k]) <= TOL * max(abs(terms[k]), 1e-30) or (terms[k] == 0.0 and t[i] == 0.0), (k, t[i], terms[k])
     for n, gv in eng.gradients().items():
         ref = grads[n]
         assert ((gv.cpu().double().reshape(ref.shape) - ref).norm() / ref.norm().clamp_min(1e-30)).item() < TOL, n
+    eng.adam_step()
     for n, pv in eng.parameters().items():
         ref = adam1[n]
         assert ((pv.cpu().double().reshape(ref.shape) - ref).norm() / ref.norm().clamp_min(1e-30)).item() < TOL, ("adam", n)

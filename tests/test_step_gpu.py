@@ -221,6 +221,37 @@ def test_graph_replay_matches_eager():
     eager.close(); graph.close()
 
 
+def test_gradient_buffer_clearing_between_steps():
+    """The training step's Adam kernel clears the gradient buffer (the next step accumulates into zeros, no memset node); an eager
+    forward_backward between two replays of a captured step leaves it dirty and the next replay must still start from zeros."""
+    cfg = CONFIGS["cfg3"]
+    spec = make_spec(cfg)
+    params = perturbed_params(spec)
+    x, _, eps, u = O.synthetic_batch(spec, cfg["batch"])
+    xs = x.to(torch.uint8).cuda(); e_d, u_d = eps.cuda(), u.cuda()
+    a = make_engine(cfg, "bf16"); a.set_parameters(params)
+    b = make_engine(cfg, "bf16"); b.set_parameters(params)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        a.train_step(xs, eps=e_d, gumbel_u=u_d)
+        assert a.grads.abs().max().item() == 0.0                 # cleared by Adam
+        a.capture_step(xs, eps=e_d, gumbel_u=u_d)
+        a.replay()
+        a.forward_backward(xs, eps=e_d, gumbel_u=u_d)            # gradients left in the buffer
+        assert a.grads.abs().max().item() > 0.0
+        a.replay()
+    side.synchronize()
+    for _ in range(3):
+        b.forward_backward(xs, eps=e_d, gumbel_u=u_d)            # the stand-alone path: clears, accumulates, Adam keeps the gradients
+        b.allreduce_grads(); b.finalize_loss(); b.adam_step()
+        assert b.grads.abs().max().item() > 0.0
+    torch.cuda.synchronize()
+    assert a.global_step == 3 and b.global_step == 3
+    d = (a.params - b.params).norm() / b.params.norm()
+    assert d.item() < 1e-4
+    a.close(); b.close()
+
+
 def test_device_noise_statistics():
     """eps / u drawn on the device (Philox) when not injected: loss stays finite and changes per step."""
     cfg = CONFIGS["cfg3"]
