@@ -53,6 +53,7 @@ SYMBOLS = {
     "gmvae_allreduce_grads": (_I, [_P, _P]),
     "gmvae_peer_export": (_I, [_P, _I, _I, C.c_char_p]),
     "gmvae_peer_attach": (_I, [_P, C.c_char_p]),
+    "gmvae_peer_grads": (_P, [_P]),
     "gmvae_train_step": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gmvae_step_graph_capture": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gmvae_step_graph_launch": (_I, [_P, _P]),

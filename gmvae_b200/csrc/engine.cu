@@ -182,6 +182,8 @@ struct gmvae_handle {
   bool peer_ready = false;
   void* peer_region = nullptr;           // this rank's symmetric region (cudaMalloc, exported through cudaIpc)
   void* peer_mapped[peer::MAX_WORLD] = {};   // other ranks' regions as mapped into this process
+  long long peer_timeout_cycles = 0;         // bound of the flag waits (GMVAE_PEER_TIMEOUT_S, default 120 s)
+  float* grads_bound = nullptr;              // the caller's gradient buffer (gmvae_bind); `grads` moves into the symmetric region on attach
   peer::Layout peer_layout;
   peer::Peers peer_ptrs;
   int64_t reduced_upto = 0;              // floats of `grads` already handed to NCCL this step
@@ -1523,7 +1525,8 @@ int gmvae_bind(gmvae_handle* h, float* params, float* grads, float* adam_m, floa
   GM_REQUIRE(workspace_bytes >= h->ws_needed, "workspace too small");
   GM_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(adam_m) && aligned16(adam_v), "buffers must be 16-byte aligned");
   GM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  h->params = params; h->grads = grads; h->adam_m = adam_m; h->adam_v = adam_v;
+  GM_REQUIRE(!h->peer_ready, "gmvae_bind after gmvae_peer_attach is not supported");
+  h->params = params; h->grads = grads; h->grads_bound = grads; h->adam_m = adam_m; h->adam_v = adam_v;
   h->ws = reinterpret_cast<uint8_t*>(workspace); h->ws_bytes = workspace_bytes;
   h->shadow_host.clear(); h->shadow_tiles = 0;
   if (h->bf16_mode()) {
@@ -1582,17 +1585,30 @@ int gmvae_finalize_loss(gmvae_handle* h, float* loss_terms, void* stream) {
 }
 
 // Adam (+ optionally the loss-term finalisation, folded into the same launch by gmvae_train_step)
-static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st, bool zero_grads) {
+static int adam_step_impl(gmvae_handle* h, float* loss_terms, cudaStream_t st, bool zero_grads, bool fused_exchange = false) {
   const gmvae_config& c = h->cfg;
   int64_t n = h->n_params;
   // after a cross-stream join (data-parallel all-reduce) the kernel is launched with a full dependency
   const bool pdl = !(h->comm && h->world > 1 && (h->debug_flags & DBG_COMM_OVERLAP));
   // one launch: parameter update, the bf16 operand copies of the weight matrices, global_step += 1, (training step) gradients cleared
   const int64_t per_block = (int64_t)ADAM_THREADS * 4 * ADAM_VEC;
-  GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n + per_block - 1) / per_block)), dim3(ADAM_THREADS), 0, st, pdl, h->params, h->grads,
+  AdamPeer ap = {nullptr, nullptr, nullptr, 0, 0};
+  float* g_src = h->grads;
+  if (fused_exchange) {
+    // last phase of the peer-memory all-reduce (peer.cuh): read the reduced gradients the shard owners pushed into this rank's
+    // `red` buffer once all of them have landed, clear this rank's own gradient buffer
+    const peer::Layout& L = h->peer_layout;
+    char* base = static_cast<char*>(h->peer_region);
+    g_src = reinterpret_cast<float*>(base + L.red_off);
+    ap.flags = reinterpret_cast<const unsigned long long*>(base + L.flags_off) + peer::MAX_WORLD;
+    ap.epoch = &reinterpret_cast<peer::Local*>(base + L.local_off)->epoch;
+    ap.own_grads = h->grads; ap.world = L.world; ap.timeout_cycles = h->peer_timeout_cycles;
+    zero_grads = true;
+  }
+  GM_CHECK_CUDA(launch_k(adam_kernel, dim3((unsigned)((n + per_block - 1) / per_block)), dim3(ADAM_THREADS), 0, st, pdl && !fused_exchange, h->params, g_src,
                          h->adam_m, h->adam_v, n, c.learning_rate, c.beta1, c.beta2, c.epsilon, h->state,
-                         h->grads + h->n_params, loss_terms, (const ShadowEntry*)h->shadow_dev,
-                         h->bf16_mode() ? (int)h->shadow_host.size() : 0, zero_grads ? 1 : 0));
+                         g_src + h->n_params, loss_terms, (const ShadowEntry*)h->shadow_dev,
+                         h->bf16_mode() ? (int)h->shadow_host.size() : 0, zero_grads ? 1 : 0, ap));
   GM_LAUNCHED(h, st, PC_ADAM);
   h->grads_clean = zero_grads;
   return 0;
@@ -1666,10 +1682,12 @@ int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int ran
   for (auto& e : h->comm_ev) GM_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
-// ---- experimental: all-reduce over NVLink peer memory (peer.cuh).  export: allocate this rank's symmetric region and hand out
-// its cudaIpc handle; attach: map every rank's region (handles in rank order, own included).  The caller puts a barrier
-// between attach and the first step.
+// ---- the exchange step over NVLink peer memory (peer.cuh).  export: allocate this rank's symmetric region (gradient buffer,
+// reduced-gradient buffer, flags) and hand out its cudaIpc handle; attach: map every rank's region (handles in rank order, own
+// included) and MOVE the handle's gradient buffer into the region (gmvae_peer_grads returns it; the caller's buffer is no longer
+// used).  The caller puts a barrier between attach and the first step.
 int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && out, "null argument");
   GM_TRY(check_ready(h));
   GM_REQUIRE(world_size >= 2 && world_size <= peer::MAX_WORLD && rank >= 0 && rank < world_size, "bad world_size / rank");
@@ -1677,7 +1695,6 @@ int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
   const int64_t total = h->n_params + ACC_SLOTS;
   GM_REQUIRE(total % 4 == 0, "gradient buffer length must be a multiple of 4 floats");
-  GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
   h->peer_layout = peer::make_layout(world_size, total);
   GM_CHECK_CUDA(cudaMalloc(&h->peer_region, h->peer_layout.bytes));
   GM_CHECK_CUDA(cudaMemset(h->peer_region, 0, h->peer_layout.bytes));
@@ -1690,9 +1707,9 @@ int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]) {
   return 0;
 }
 int gmvae_peer_attach(gmvae_handle* h, const char* handles) {
+  DeviceGuard dev_guard(h);
   GM_REQUIRE(h && handles, "null argument");
   GM_REQUIRE(h->peer_region && !h->peer_ready, "call gmvae_peer_export first (once)");
-  GM_CHECK_CUDA(cudaSetDevice(h->cfg.device));
   const peer::Layout& L = h->peer_layout;
   for (int r = 0; r < L.world; ++r) {
     void* base = h->peer_region;
@@ -1703,29 +1720,50 @@ int gmvae_peer_attach(gmvae_handle* h, const char* handles) {
       h->peer_mapped[r] = base;
     }
     char* b = static_cast<char*>(base);
-    h->peer_ptrs.recv[r] = reinterpret_cast<float4*>(b + L.recv_off);
+    h->peer_ptrs.grad[r] = reinterpret_cast<float4*>(b + L.grad_off);
     h->peer_ptrs.red[r] = reinterpret_cast<float4*>(b + L.red_off);
     h->peer_ptrs.flags[r] = reinterpret_cast<unsigned long long*>(b + L.flags_off);
   }
+  const char* ts = getenv("GMVAE_PEER_TIMEOUT_S");
+  const double secs = ts ? std::max(1.0, atof(ts)) : 120.0;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
+  h->peer_timeout_cycles = (long long)(secs * 1e3 * (double)std::max(khz, 1000000));
+  // the backward pass now accumulates straight into the symmetric region (zero from the memset at export)
+  h->grads_bound = h->grads;
+  h->grads = reinterpret_cast<float*>(static_cast<char*>(h->peer_region) + L.grad_off);
+  h->grads_clean = true;
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured with the old pointers
   h->peer_ready = true;
   return 0;
 }
-static int peer_allreduce(gmvae_handle* h, cudaStream_t st) {
+// The gradient buffer after gmvae_peer_attach (float[grad_count] inside the symmetric region), or the bound one.
+float* gmvae_peer_grads(gmvae_handle* h) { return h ? h->grads : nullptr; }
+
+static int peer_exchange(gmvae_handle* h, cudaStream_t st) {
   const peer::Layout& L = h->peer_layout;
   peer::Local* loc = reinterpret_cast<peer::Local*>(static_cast<char*>(h->peer_region) + L.local_off);
-  auto grid = [&](int64_t items) { return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((items + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()))); };
-  float4* g = reinterpret_cast<float4*>(h->grads);
-  GM_CHECK_CUDA(launch_k(peer::push_kernel, grid(L.n4), dim3(peer::THREADS), 0, st, false, (const float4*)g, L, h->rank, h->peer_ptrs, loc));
-  GM_CHECK_CUDA(launch_k(peer::reduce_kernel, grid(L.cap4), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc));
-  GM_CHECK_CUDA(launch_k(peer::gather_kernel, grid(L.n4), dim3(peer::THREADS), 0, st, false, g, L, h->rank, h->peer_ptrs, loc));
-  h->launches += 3;
+  const int64_t items = L.cap4;
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((items + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()));
+  GM_CHECK_CUDA(launch_k(peer::exchange_kernel, dim3(blocks), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc, h->peer_timeout_cycles));
+  GM_LAUNCHED(h, st, PC_COMM);
   return 0;
 }
 
 int gmvae_allreduce_grads(gmvae_handle* h, void* stream) {
   DeviceGuard dev_guard(h);
   GM_TRY(check_ready(h));
-  if (h->peer_ready && h->world > 1) return peer_allreduce(h, (cudaStream_t)stream);
+  if (h->peer_ready && h->world > 1) {
+    // stand-alone form: exchange, then the reduced gradients are copied back over this rank's gradient buffer
+    GM_TRY(peer_exchange(h, (cudaStream_t)stream));
+    const peer::Layout& L = h->peer_layout;
+    peer::Local* loc = reinterpret_cast<peer::Local*>(static_cast<char*>(h->peer_region) + L.local_off);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L.n4 + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()));
+    GM_CHECK_CUDA(launch_k(peer::gather_kernel, dim3(blocks), dim3(peer::THREADS), 0, (cudaStream_t)stream, false, L, h->rank, h->peer_ptrs, loc,
+                           h->peer_timeout_cycles));
+    GM_LAUNCHED(h, (cudaStream_t)stream, PC_COMM);
+    return 0;
+  }
   if (!h->comm || h->world == 1) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = h->n_params + ACC_SLOTS;
@@ -1752,10 +1790,11 @@ int gmvae_train_step(gmvae_handle* h, const uint8_t* x_u8, int batch, int global
   h->in_train_step = true;
   int r = gmvae_forward_backward(h, x_u8, batch, global_batch, eps, gumbel_u, stream);
   h->in_train_step = false;
-  if (r == 0) r = gmvae_allreduce_grads(h, stream);
+  const bool fused = h->peer_ready && h->world > 1;             // exchange kernel + Adam as the all-reduce's last phase (peer.cuh)
+  if (r == 0) r = fused ? peer_exchange(h, (cudaStream_t)stream) : gmvae_allreduce_grads(h, stream);
   h->overlap_comm = false;
   GM_TRY(r);
-  return adam_step_impl(h, loss_terms, (cudaStream_t)stream, true);
+  return adam_step_impl(h, loss_terms, (cudaStream_t)stream, true, fused);
 }
 
 int gmvae_step_graph_capture(gmvae_handle* h, const uint8_t* x_u8, int batch, int global_batch, const float* eps,

@@ -1075,21 +1075,47 @@ __global__ void finalize_loss_kernel(const float* __restrict__ acc, float* __res
 // Also (training step only, `zero_grads`): the gradient buffer and the loss accumulators are cleared once read, so the next step
 // starts from zeros without a separate memset node.  8 elements per thread, every load issued before the block waits for lr_t.
 constexpr int ADAM_THREADS = 256, ADAM_VEC = 2;              // float4 groups per thread
+struct AdamPeer {                                            // all null / 0 outside the peer-memory data-parallel path
+  const unsigned long long* flags;                           // [world] "shard r of the reduced gradients has landed" epochs (my memory)
+  unsigned long long* epoch;                                 // the exchange epoch counter of this rank
+  float* own_grads;                                          // this rank's gradient buffer (cleared here)
+  int world; long long timeout_cycles;
+};
 __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float lr, float b1, float b2, float eps, DeviceState* st,
                             float* __restrict__ acc, float* __restrict__ loss_out,
-                            const ShadowEntry* __restrict__ shadows, int n_shadows, int zero_grads) {
+                            const ShadowEntry* __restrict__ shadows, int n_shadows, int zero_grads, AdamPeer peer) {
   griddep_wait();
   griddep_launch();
   __shared__ float lr_t_s;
   __shared__ int e0_s;
+  // Data parallel over peer memory (peer.cuh): this launch is the last phase of the all-reduce.  `g` is the reduced-gradient
+  // buffer the shard owners push into; wait until all `world` shards of this epoch have landed (one polling thread per block).
+  // `gz` is what gets cleared: this rank's own gradient buffer (every owner has pulled from it before publishing its shard).
+  float* gz = g;
+  float* accz = acc;
+  if (peer.flags) {
+    if (threadIdx.x == 0) {
+      const unsigned long long epoch = *peer.epoch + 1;
+      const long long t0 = clock64();
+      for (int r = 0; r < peer.world; ++r) {
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(peer.flags + r) : "memory");
+          if (v < epoch) { __nanosleep(64); if (clock64() - t0 > peer.timeout_cycles) __trap(); }
+        } while (v < epoch);
+      }
+    }
+    __syncthreads();
+    gz = peer.own_grads; accz = peer.own_grads + n;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 32) {
     if (loss_out) {                                          // loss terms (gmvae.py:267 / vae.py:185), same as finalize_loss_kernel
       float nll = acc_total(acc, ACC_NLL), kl = acc_total(acc, ACC_KL), ne = acc_total(acc, ACC_NENT);
       loss_out[0] = nll + kl + ne; loss_out[1] = nll; loss_out[2] = kl; loss_out[3] = ne;
     }
     if (zero_grads)
-      for (int i = 0; i < ACC_SLOTS; ++i) acc[i] = 0.f;
+      for (int i = 0; i < ACC_SLOTS; ++i) accz[i] = 0.f;
   }
   const int64_t i0 = (int64_t)blockIdx.x * ADAM_THREADS * 4 * ADAM_VEC;
   // operands first: the loads are in flight while thread 0 works out the step size
@@ -1099,7 +1125,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ 
   for (int u = 0; u < ADAM_VEC; ++u) {
     idx[u] = i0 + ((int64_t)u * ADAM_THREADS + threadIdx.x) * 4;
     if (idx[u] + 4 <= n) {
-      pp[u] = *reinterpret_cast<float4*>(p + idx[u]); gg[u] = *reinterpret_cast<const float4*>(g + idx[u]);
+      pp[u] = *reinterpret_cast<float4*>(p + idx[u]); gg[u] = __ldcg(reinterpret_cast<const float4*>(g + idx[u]));
       mm[u] = *reinterpret_cast<float4*>(m + idx[u]); vv[u] = *reinterpret_cast<float4*>(v + idx[u]);
     }
   }
@@ -1109,7 +1135,10 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ 
     lr_t_s = (float)((double)lr * sqrt(1.0 - b2t) / (1.0 - b1t));
     // global_step += 1 and the powers advance once every block of this launch has read them: the last block to get here does it
     __threadfence();
-    if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) { st->adam_blocks = 0; st->step += 1; st->beta1_power = b1t; st->beta2_power = b2t; }
+    if (atomicAdd(&st->adam_blocks, 1u) == gridDim.x - 1) {
+      st->adam_blocks = 0; st->step += 1; st->beta1_power = b1t; st->beta2_power = b2t;
+      if (peer.flags) *peer.epoch += 1;                      // every block of this launch has passed its wait: the exchange epoch is over
+    }
   } else if (threadIdx.x == 64) {
     // the weight matrix the block's first element belongs to (entries are sorted by flat offset); the block's
     // elements almost always lie in the same matrix, so the threads only step forward from here
@@ -1141,7 +1170,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ 
         P[j] -= lr_t * Mm[j] / (sqrtf(V[j]) + eps);
       }
       *reinterpret_cast<float4*>(p + i) = pp[u]; *reinterpret_cast<float4*>(m + i) = mm[u]; *reinterpret_cast<float4*>(v + i) = vv[u];
-      if (zero_grads) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zero_grads) *reinterpret_cast<float4*>(gz + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       if (wb) {                                               // bf16 GEMM operand copy [rows, ld_w] of the updated weights
         if (cols == ld_w && rel + 4 <= lim) {
           *reinterpret_cast<uint2*>(wb + rel) = make_uint2(pack_bf16x2(P[0], P[1]), pack_bf16x2(P[2], P[3]));
@@ -1155,11 +1184,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_kernel(float* __restrict__ 
       }
     } else {
       for (int64_t k = i; k < n; ++k) {
-        float mk = b1 * m[k] + (1.f - b1) * g[k];
-        float vk = b2 * v[k] + (1.f - b2) * g[k] * g[k];
+        const float gk = __ldcg(g + k);
+        float mk = b1 * m[k] + (1.f - b1) * gk;
+        float vk = b2 * v[k] + (1.f - b2) * gk * gk;
         m[k] = mk; v[k] = vk;
         p[k] -= lr_t * mk / (sqrtf(vk) + eps);
-        if (zero_grads) g[k] = 0.f;
+        if (zero_grads) gz[k] = 0.f;
         if (wb) { const int64_t el = rel + (k - i); if (el < lim) wb[(el / cols) * ld_w + (el % cols)] = __float2bfloat16_rn(p[k]); }
       }
     }

@@ -343,19 +343,28 @@ class Engine:
         dist.broadcast_object_list(obj, src=0)
         _lib.check(self.lib.gmvae_nccl_init(self._h, obj[0], self.world_size, self.rank), "gmvae_nccl_init")
         import os
-        if os.environ.get("GMVAE_DP_PEER") == "1":
+        if os.environ.get("GMVAE_DP_PEER", "1") != "0":
             self.attach_peers()
 
     def attach_peers(self):
-        """EXPERIMENTAL, off by default: replace the NCCL all-reduce of the step by the library's own two-shot all-reduce
-        over NVLink peer memory (csrc/peer.cuh).  Every rank exports its symmetric region, the cudaIpc handles travel
-        through torch.distributed, and a barrier separates attaching from the first step."""
+        """The exchange step over NVLink peer memory, fused with Adam (csrc/peer.cuh), in place of the NCCL all-reduce (default
+        under data parallelism; GMVAE_DP_PEER=0 keeps NCCL).  Every rank exports its symmetric region, the cudaIpc handles travel
+        through torch.distributed, and a barrier separates attaching from the first step.  The gradient buffer moves into the
+        region: `self.grads` is re-pointed at it (zero-copy view of library-owned memory)."""
         import torch.distributed as dist
         buf = C.create_string_buffer(64)
         _lib.check(self.lib.gmvae_peer_export(self._h, self.world_size, self.rank, buf), "gmvae_peer_export")
         handles = [None] * self.world_size
         dist.all_gather_object(handles, bytes(buf.raw))
         _lib.check(self.lib.gmvae_peer_attach(self._h, b"".join(handles)), "gmvae_peer_attach")
+        ptr = self.lib.gmvae_peer_grads(self._h)
+
+        class _Raw:                                              # torch.as_tensor understands the CUDA array interface: no copy
+            __cuda_array_interface__ = {"shape": (int(self.grads.numel()),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        with torch.cuda.device(self.device):
+            self._grads_bound = self.grads
+            self.grads = torch.as_tensor(_Raw(), device=self.device)
+        self._graph_ready = False
         dist.barrier()
 
     PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc", "comm"]

@@ -128,13 +128,17 @@ GMVAE_API int gmvae_nccl_unique_id(char out[128]);
 GMVAE_API int gmvae_nccl_init(gmvae_handle* h, const char id[128], int world_size, int rank);
 GMVAE_API int gmvae_allreduce_grads(gmvae_handle* h, void* stream);
 
-/* EXPERIMENTAL (off unless attached): gmvae_allreduce_grads as the library's own kernels over NVLink peer memory --
- * a two-shot all-reduce (reduce-scatter by push, all-gather by push; csrc/peer.cuh) in place of ncclAllReduce.
- * export() allocates this rank's symmetric region and returns its cudaIpcMemHandle_t (64 bytes); the caller gathers
- * the handles of all ranks (rank order, own included), passes them to attach() and puts a barrier before the first
- * step.  One node, P2P-capable GPUs, world_size <= 16. */
+/* The exchange step as the library's own kernels over NVLink peer memory, fused with the optimiser (csrc/peer.cuh), in place of
+ * ncclAllReduce: every rank's gradient buffer lives in a symmetric region all ranks map (cudaIpc); one `exchange` kernel per step
+ * pulls this rank's shard of every rank's gradients, adds them in rank order and pushes the sums to every rank, and the Adam kernel
+ * is the all-reduce's last phase (it waits for the shards, reads the reduced gradients, clears this rank's buffer).
+ * export() allocates this rank's region and returns its cudaIpcMemHandle_t (64 bytes); the caller gathers the handles of all ranks
+ * (rank order, own included), passes them to attach() and puts a barrier before the first step.  attach() MOVES the gradient buffer
+ * into the region: gmvae_peer_grads() is where the gradients are from then on (float[grad_count]); steps captured before are
+ * dropped.  One node, P2P-capable GPUs, world_size <= 16.  Flag waits are bounded by GMVAE_PEER_TIMEOUT_S (default 120 s). */
 GMVAE_API int gmvae_peer_export(gmvae_handle* h, int world_size, int rank, char out[64]);
 GMVAE_API int gmvae_peer_attach(gmvae_handle* h, const char* handles);
+GMVAE_API float* gmvae_peer_grads(gmvae_handle* h);
 
 /* One whole iteration of the hot loop `sess.run([train_op, global_step])`
  * (runners.py:231-232): forward_backward -> allreduce -> finalize_loss -> adam_step.

@@ -1,12 +1,12 @@
 // Concurrency model of the peer-memory all-reduce protocol (gmvae_b200/csrc/peer.cuh), run on the CPU under ThreadSanitizer.
 //
 // peer.cuh's kernels synchronise ranks with epoch flags (st.release.sys / ld.acquire.sys), publish them from the last block of
-// a grid (fence + ticket counter) and reuse single receive / reduced buffers across steps.  This program restates exactly that
-// protocol with host atomics -- one std::thread per (rank, block); the kernels of one rank are separated by a per-rank barrier
-// (stream order); NOTHING orders different ranks except the flags -- and uses peer.cuh's own layout and element functions for
-// the data movement.  Plain (non-atomic) accesses to the buffers make every missing happens-before edge a TSan report; random
-// delays shake the interleavings; every rank checks every step's result.  It validates the protocol's design (no deadlock,
-// no race when buffers are reused by the next step), not the CUDA code itself.  Test infrastructure.
+// a grid (fence + ticket counter) and reuse the gradient / reduced buffers across steps without double buffering.  This program
+// restates exactly that protocol with host atomics -- one std::thread per (rank, block); the kernels of one rank are separated by a
+// per-rank barrier (stream order); NOTHING orders different ranks except the flags -- and uses peer.cuh's own layout and element
+// functions for the data movement.  Plain (non-atomic) accesses to the buffers make every missing happens-before edge a TSan
+// report; random delays shake the interleavings; every rank checks every step's result.  It validates the protocol's design (no
+// deadlock, no race when buffers are reused by the next step), not the CUDA code itself.  Test infrastructure.
 //
 //   host_peer_protocol <world> <n_floats> <steps> <blocks_per_rank>      exit code 0 = all ranks saw the exact sums
 #include <atomic>
@@ -27,7 +27,6 @@ static float value_of(int rank, int step, int64_t i) { return (float)((rank + 1)
 
 struct Rank {
   std::vector<char> region;
-  std::vector<float> grads;
   std::unique_ptr<std::barrier<>> stream;     // kernel boundaries of this rank (stream order)
 };
 
@@ -41,7 +40,7 @@ static bool last_block_host(unsigned int* done, int nblocks) {
   if (last) __atomic_store_n(done, 0u, __ATOMIC_RELAXED);
   return last;
 }
-static int g_mutation = 0;   // PEER_MUTATE: 1 = gather does not wait for the reduced shards, 2 = reduce does not wait for the pushes
+static int g_mutation = 0;   // PEER_MUTATE: 1 = Adam does not wait for the landed shards, 2 = the exchange does not wait for the gradients
 static void wait_epochs_host(const unsigned long long* flags, int world, unsigned long long epoch) {
   for (int r = 0; r < world; ++r)
     while (ld_acquire(flags + r) < epoch) std::this_thread::yield();
@@ -59,9 +58,8 @@ int main(int argc, char** argv) {
   Peers P;
   for (int r = 0; r < world; ++r) {
     ranks[r].region.assign(L.bytes, 0);
-    ranks[r].grads.assign(n, 0.f);
     ranks[r].stream = std::make_unique<std::barrier<>>(blocks);
-    P.recv[r] = reinterpret_cast<float4*>(ranks[r].region.data() + L.recv_off);
+    P.grad[r] = reinterpret_cast<float4*>(ranks[r].region.data() + L.grad_off);
     P.red[r] = reinterpret_cast<float4*>(ranks[r].region.data() + L.red_off);
     P.flags[r] = reinterpret_cast<unsigned long long*>(ranks[r].region.data() + L.flags_off);
   }
@@ -71,47 +69,41 @@ int main(int argc, char** argv) {
     auto jitter = [&]() { if (rng() % 4 == 0) std::this_thread::sleep_for(std::chrono::microseconds(rng() % 200)); };
     Rank& me = ranks[rank];
     Local* loc = reinterpret_cast<Local*>(me.region.data() + L.local_off);
-    float4* g = reinterpret_cast<float4*>(me.grads.data());
+    float4* g = P.grad[rank];
     for (int step = 0; step < steps; ++step) {
-      // "backward pass": this block's part of the gradients
-      for (int64_t i4 = block; i4 < L.n4; i4 += blocks) g[i4] = make_float4(value_of(rank, step, 4 * i4), value_of(rank, step, 4 * i4 + 1), value_of(rank, step, 4 * i4 + 2), value_of(rank, step, 4 * i4 + 3));
+      // "backward pass": this block's part of the gradients, ACCUMULATED into the (cleared) buffer
+      for (int64_t i4 = block; i4 < L.n4; i4 += blocks) {
+        g[i4].x += value_of(rank, step, 4 * i4); g[i4].y += value_of(rank, step, 4 * i4 + 1);
+        g[i4].z += value_of(rank, step, 4 * i4 + 2); g[i4].w += value_of(rank, step, 4 * i4 + 3);
+      }
       me.stream->arrive_and_wait();
       jitter();
-      // ---- push_kernel
-      unsigned long long epoch = loc->epoch + 1;      // written by this rank's gather of the previous step, ordered by the stream barrier
-      for (int64_t i4 = block; i4 < L.n4; i4 += blocks) {
-        int owner; int64_t dst4;
-        push_target(L, rank, i4, owner, dst4);
-        P.recv[owner][dst4] = g[i4];
+      // ---- exchange_kernel
+      unsigned long long epoch = loc->epoch + 1;      // advanced by this rank's Adam of the previous step, ordered by the stream barrier
+      if (block == 0)
+        for (int r = 0; r < world; ++r) st_release(P.flags[r] + rank, epoch);                    // (a) my gradients are final
+      if (g_mutation != 2) wait_epochs_host(P.flags[rank], world, epoch);                        // (b)
+      const int64_t b4 = shard_begin4(L, rank);
+      for (int64_t i = block; i < shard_len4(L, rank); i += blocks) {                            // (c) pull, add, push
+        const float4 s = reduce_ranks(L, P, b4 + i, LoadPeer());
+        for (int p = 0; p < world; ++p) P.red[p][b4 + i] = s;
       }
       if (last_block_host(&loc->done[0], blocks))
-        for (int r = 0; r < world; ++r) st_release(P.flags[r] + rank, epoch);
+        for (int r = 0; r < world; ++r) st_release(P.flags[r] + MAX_WORLD + rank, epoch);        // (d) shard `rank` has landed
       me.stream->arrive_and_wait();
       jitter();
-      // ---- reduce_kernel
-      if (g_mutation != 2) wait_epochs_host(P.flags[rank], world, epoch);
-      for (int64_t i = block; i < shard_len4(L, rank); i += blocks) {
-        const float4 s = reduce_slots(L, P.recv[rank], i, LoadPeerWritten());
-        for (int p = 0; p < world; ++p) P.red[p][red_index(L, rank, i)] = s;
-      }
-      if (last_block_host(&loc->done[1], blocks))
-        for (int r = 0; r < world; ++r) st_release(P.flags[r] + MAX_WORLD + rank, epoch);
-      me.stream->arrive_and_wait();
-      jitter();
-      // ---- gather_kernel
+      // ---- adam_kernel: wait for the shards, read the reduced gradients, clear my own gradient buffer
       if (g_mutation != 1) wait_epochs_host(P.flags[rank] + MAX_WORLD, world, epoch);
-      for (int64_t i4 = block; i4 < L.n4; i4 += blocks) g[i4] = P.red[rank][i4];
-      if (last_block_host(&loc->done[2], blocks)) loc->epoch = epoch;
-      me.stream->arrive_and_wait();
-      // ---- "Adam": check what arrived
       for (int64_t i4 = block; i4 < L.n4; i4 += blocks) {
-        const float* v = reinterpret_cast<const float*>(g + i4);
+        const float* v = reinterpret_cast<const float*>(P.red[rank] + i4);
         for (int c = 0; c < 4; ++c) {
           float want = 0.f;
           for (int r = 0; r < world; ++r) want += value_of(r, step, 4 * i4 + c);
           if (v[c] != want) errors.fetch_add(1);
         }
+        g[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (last_block_host(&loc->done[2], blocks)) loc->epoch = epoch;
       me.stream->arrive_and_wait();
     }
   };

@@ -1,7 +1,7 @@
-"""The experimental peer-memory all-reduce (gmvae_b200/csrc/peer.cuh; off by default): its layout and element
-arithmetic, compiled for the host (tests/native/host_peer.cu) and run for `world` simulated ranks, equal a rank-ordered
-fp32 sum on every rank, bit for bit -- including ragged last shards and buffers shorter than the world size.  The
-synchronisation (system-scope flags over NVLink) is not covered here; it needs GPUs."""
+"""The peer-memory all-reduce fused with Adam (gmvae_b200/csrc/peer.cuh): its layout and element arithmetic, compiled for the host
+(tests/native/host_peer.cu) and run for `world` simulated ranks, equal a rank-ordered fp32 sum on every rank, bit for bit --
+including ragged last shards and buffers shorter than the world size; and its synchronisation protocol as a host model under
+ThreadSanitizer.  The CUDA kernels themselves run on 2 / 8 B200s through tools/dp_check.py (profiles/r2_dp_check_*.json)."""
 import ctypes as C
 import os
 import shutil
@@ -35,7 +35,7 @@ def test_simulated_ranks_agree_with_rank_ordered_sum(host_peer, world, n):
     g = rng.standard_normal((world, n)).astype(np.float32)
     want = g[0].copy()
     for r in range(1, world):
-        want = want + g[r]                                             # fp32, rank order: what reduce_slots does
+        want = want + g[r]                                             # fp32, rank order: what reduce_ranks does
     buf = np.ascontiguousarray(g.copy())
     assert host_peer.host_peer_allreduce(world, n, buf.ctypes.data) == 0
     for r in range(world):
@@ -84,8 +84,8 @@ def test_protocol_is_race_free_and_exact_over_many_steps(protocol_exe, world, n,
 
 @pytest.mark.parametrize("mutate", [1, 2])
 def test_protocol_model_detects_a_missing_wait(protocol_exe, mutate):
-    """The detector works: dropping either wait (reduce without the pushes' flags, gather without the reduced
-    shards' flags) is reported as a data race and / or wrong sums."""
+    """The detector works: dropping either wait (the exchange without the gradients-final flags, Adam without the landed-shard
+    flags) is reported as a data race and / or wrong sums."""
     r = _run_protocol(protocol_exe, 4, 4096, 20, 3, mutate=mutate)
     assert r.returncode != 0
     assert "ThreadSanitizer: data race" in r.stderr or '"errors": 0' not in r.stdout
