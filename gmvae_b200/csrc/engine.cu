@@ -1743,7 +1743,7 @@ float* gmvae_peer_grads(gmvae_handle* h) { return h ? h->grads : nullptr; }
 static int peer_exchange(gmvae_handle* h, cudaStream_t st) {
   const peer::Layout& L = h->peer_layout;
   peer::Local* loc = reinterpret_cast<peer::Local*>(static_cast<char*>(h->peer_region) + L.local_off);
-  const int64_t items = L.cap4;
+  const int64_t items = (L.cap4 + 3) / 4;                          // four float4 per thread and pass
   const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((items + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()));
   GM_CHECK_CUDA(launch_k(peer::exchange_kernel, dim3(blocks), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc, h->peer_timeout_cycles));
   GM_LAUNCHED(h, st, PC_COMM);
