@@ -1743,9 +1743,11 @@ float* gmvae_peer_grads(gmvae_handle* h) { return h ? h->grads : nullptr; }
 static int peer_exchange(gmvae_handle* h, cudaStream_t st) {
   const peer::Layout& L = h->peer_layout;
   peer::Local* loc = reinterpret_cast<peer::Local*>(static_cast<char*>(h->peer_region) + L.local_off);
-  const int64_t items = (L.cap4 + 3) / 4;                          // four float4 per thread and pass
-  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((items + peer::THREADS - 1) / peer::THREADS, 4 * tc::num_sms()));
-  GM_CHECK_CUDA(launch_k(peer::exchange_kernel, dim3(blocks), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc, h->peer_timeout_cycles));
+  const int per_block = peer::exchange_block_items(L.world);
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L.cap4 + per_block - 1) / per_block, 8 * tc::num_sms()));
+  auto kern = L.world == 2 ? peer::exchange_kernel<2> : L.world == 4 ? peer::exchange_kernel<4> : L.world == 8 ? peer::exchange_kernel<8>
+            : L.world == 16 ? peer::exchange_kernel<16> : peer::exchange_kernel<0>;
+  GM_CHECK_CUDA(launch_k(kern, dim3(blocks), dim3(peer::THREADS), 0, st, false, L, h->rank, h->peer_ptrs, loc, h->peer_timeout_cycles));
   GM_LAUNCHED(h, st, PC_COMM);
   return 0;
 }

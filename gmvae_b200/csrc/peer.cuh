@@ -112,40 +112,70 @@ __device__ __forceinline__ bool last_block(unsigned int* done) {
   return last;
 }
 
+// volatile: the loads of a pass stay in program order ahead of the additions (all of them in flight together)
+__device__ __forceinline__ float4 ld_peer_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// W = world size known at compile time (2, 4, 8: every rank's loads of a pass are in flight together -- a peer load is a ~2 us
+// NVLink round trip, and a loop over the ranks would pay it `world` times) or 0 (any world size: one rank at a time).
+template <int W>
 __global__ void __launch_bounds__(THREADS) exchange_kernel(Layout L, int rank, Peers P, Local* loc, long long timeout_cycles) {
   const unsigned long long epoch = loc->epoch + 1;
   // (a) this kernel is stream-ordered after the backward pass: my gradients are final and visible
   if (blockIdx.x == 0 && threadIdx.x < L.world) { __threadfence_system(); st_release_sys(P.flags[threadIdx.x] + rank, epoch); }
   // (b) every rank's gradients are final
   wait_epochs(P.flags[rank], L.world, epoch, timeout_cycles);
-  // (c) my shard: pull, add in rank order, push to everybody
-  // (a peer load takes ~2 us over NVLink: four float4 per thread and rank are requested before the first is used)
+  // (c) my shard: pull, add in rank order (the same bits on every replica), push to everybody
   const int64_t b4 = shard_begin4(L, rank), len4 = shard_len4(L, rank);
-  constexpr int U = 4;
-  for (int64_t i0 = (int64_t)blockIdx.x * THREADS * U + threadIdx.x; i0 < len4; i0 += (int64_t)gridDim.x * THREADS * U) {
-    float4 s[U];
+  if constexpr (W > 0) {
+    // thread (e, r) of a block loads element e of rank r's gradients -- one NVLink round trip for all ranks -- and, after the
+    // exchange through shared memory, adds the W values of its element in rank order and stores the sum to rank r's `red`
+    constexpr int EPB = THREADS / W;                           // elements (float4) per block and pass
+    __shared__ float4 sh[THREADS];
+    const int e = threadIdx.x / W, r = threadIdx.x % W;
+    for (int64_t i0 = (int64_t)blockIdx.x * EPB; i0 < len4; i0 += (int64_t)gridDim.x * EPB) {
+      const int64_t i = i0 + e;
+      if (i < len4) sh[e * W + r] = ld_peer_v4(P.grad[r] + b4 + i);
+      __syncthreads();
+      if (i < len4) {
+        float4 s = sh[e * W];
 #pragma unroll
-    for (int u = 0; u < U; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < L.world; ++r) {                       // rank order: the same bits on every replica
-      float4 t[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i0 + u * THREADS < len4) t[u] = __ldcg(P.grad[r] + b4 + i0 + u * THREADS);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i0 + u * THREADS < len4) {
-          if (r == 0) s[u] = t[u];
-          else { s[u].x += t[u].x; s[u].y += t[u].y; s[u].z += t[u].z; s[u].w += t[u].w; }
-        }
+        for (int q = 1; q < W; ++q) { const float4 t = sh[e * W + q]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        P.red[r][b4 + i] = s;
+      }
+      __syncthreads();
     }
-    for (int p = 0; p < L.world; ++p)
+  } else {
+    constexpr int U = 4;                                       // float4 per thread, rank and pass
+    for (int64_t i0 = (int64_t)blockIdx.x * THREADS * U + threadIdx.x; i0 < len4; i0 += (int64_t)gridDim.x * THREADS * U) {
+      float4 s[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i0 + u * THREADS < len4) P.red[p][b4 + i0 + u * THREADS] = s[u];
+      for (int u = 0; u < U; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < L.world; ++r) {
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * THREADS < len4) t[u] = __ldcg(P.grad[r] + b4 + i0 + u * THREADS);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * THREADS < len4) {
+            if (r == 0) s[u] = t[u];
+            else { s[u].x += t[u].x; s[u].y += t[u].y; s[u].z += t[u].z; s[u].w += t[u].w; }
+          }
+      }
+      for (int p = 0; p < L.world; ++p)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * THREADS < len4) P.red[p][b4 + i0 + u * THREADS] = s[u];
+    }
   }
   // (d) shard `rank` has landed everywhere
   if (last_block(&loc->done[0]) && threadIdx.x < L.world) st_release_sys(P.flags[threadIdx.x] + MAX_WORLD + rank, epoch);
 }
+// float4 elements a block covers per pass
+constexpr int exchange_block_items(int world) { return (world == 2 || world == 4 || world == 8 || world == 16) ? THREADS / world : THREADS * 4; }
 
 // Stand-alone form of the last phase (gmvae_allreduce_grads without the fused Adam): reduced gradients -> my gradient buffer.
 __global__ void __launch_bounds__(THREADS) gather_kernel(Layout L, int rank, Peers P, Local* loc, long long timeout_cycles) {
