@@ -132,18 +132,26 @@ __global__ void __launch_bounds__(THREADS) exchange_kernel(Layout L, int rank, P
   if constexpr (W > 0) {
     // thread (e, r) of a block loads element e of rank r's gradients -- one NVLink round trip for all ranks -- and, after the
     // exchange through shared memory, adds the W values of its element in rank order and stores the sum to rank r's `red`
-    constexpr int EPB = THREADS / W;                           // elements (float4) per block and pass
-    __shared__ float4 sh[THREADS];
+    constexpr int EPB = THREADS / W;                           // elements (float4) per block and sub-pass
+    constexpr int U = W <= 2 ? 4 : 2;                          // sub-passes whose loads are in flight together
+    __shared__ float4 sh[U][THREADS];
     const int e = threadIdx.x / W, r = threadIdx.x % W;
-    for (int64_t i0 = (int64_t)blockIdx.x * EPB; i0 < len4; i0 += (int64_t)gridDim.x * EPB) {
-      const int64_t i = i0 + e;
-      if (i < len4) sh[e * W + r] = ld_peer_v4(P.grad[r] + b4 + i);
-      __syncthreads();
-      if (i < len4) {
-        float4 s = sh[e * W];
+    for (int64_t i0 = (int64_t)blockIdx.x * EPB * U; i0 < len4; i0 += (int64_t)gridDim.x * EPB * U) {
+      float4 t[U];
 #pragma unroll
-        for (int q = 1; q < W; ++q) { const float4 t = sh[e * W + q]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
-        P.red[r][b4 + i] = s;
+      for (int u = 0; u < U; ++u) t[u] = ld_peer_v4(P.grad[r] + b4 + min(i0 + u * EPB + e, len4 - 1));   // (clamped: the tail re-reads the last element)
+#pragma unroll
+      for (int u = 0; u < U; ++u) sh[u][e * W + r] = t[u];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * EPB + e;
+        if (i < len4) {
+          float4 s = sh[u][e * W];
+#pragma unroll
+          for (int q = 1; q < W; ++q) { const float4 v = sh[u][e * W + q]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+          P.red[r][b4 + i] = s;
+        }
       }
       __syncthreads();
     }
@@ -175,7 +183,9 @@ __global__ void __launch_bounds__(THREADS) exchange_kernel(Layout L, int rank, P
   if (last_block(&loc->done[0]) && threadIdx.x < L.world) st_release_sys(P.flags[threadIdx.x] + MAX_WORLD + rank, epoch);
 }
 // float4 elements a block covers per pass
-constexpr int exchange_block_items(int world) { return (world == 2 || world == 4 || world == 8 || world == 16) ? THREADS / world : THREADS * 4; }
+constexpr int exchange_block_items(int world) {
+  return world == 2 ? (THREADS / 2) * 4 : (world == 4 || world == 8 || world == 16) ? (THREADS / world) * 2 : THREADS * 4;
+}
 
 // Stand-alone form of the last phase (gmvae_allreduce_grads without the fused Adam): reduced gradients -> my gradient buffer.
 __global__ void __launch_bounds__(THREADS) gather_kernel(Layout L, int rank, Peers P, Local* loc, long long timeout_cycles) {
