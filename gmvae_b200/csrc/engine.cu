@@ -134,8 +134,8 @@ enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8
                               pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
                               vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
        DBG_NO_PAIR = 65536 /* run the one-launch plan on single CTAs (tcgen05 cta_group::1, 128 x 256 tiles) instead of CTA pairs */,
-       DBG_RELU_BITS = 2048 /* 1-bit ReLU masks between the chained forward and backward jobs: measured 1 % slower than
-                               reading the bf16 activation through TMA, kept as an experiment */ };
+       DBG_NO_RELU_BITS = 2048 /* one-launch plan: read the ReLU mask of the backward pass from the bf16 activation (TMA load in the epilogue)
+                                  instead of the 1-bit masks the forward epilogues write */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
 enum { PC_START = -1, PC_TC_GEMM = 0, PC_TC_WGRAD = 1, PC_SIMT_GEMM = 2, PC_HEADS = 3, PC_BIAS_GRAD = 4, PC_ADAM = 5, PC_MISC = 6,
        PC_COMM = 7, PC_COUNT = 8 };
@@ -815,7 +815,7 @@ static int mlp_hidden_fwd(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, co
     int64_t ld = i == 0 ? ld0 : ldp(m.layers[i - 1].out);
     LinView L = view(h, m.layers[i], 0, i == 0 ? in0_cols : -1);
     EpiStore<A> epi{b.hid[i], (int64_t)ldp(m.layers[i].out), L.b, nullptr, 0, 1, 1.f};
-    if (tc::CHAIN_RELU_BITS && h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = b.bits[i]; epi.ld_bits = round_up(M, 32); }
+    if (tc::CHAIN_RELU_BITS && h->chain_on && h->row_jobs && !(h->debug_flags & DBG_NO_RELU_BITS)) { epi.relu_bits = b.bits[i]; epi.ld_bits = round_up(M, 32); }
     GM_TRY(lin_fwd<A>(h, in, ld, M, L, epi, st));
     h->relu_bits_valid[b.hid[i]] = epi.relu_bits != nullptr && h->last_gemm_chained;
   }
@@ -988,7 +988,7 @@ static int forward_encoder(gmvae_handle* h, const uint8_t* x_u8, int B, float in
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
       } else {
         EpiStore<A> epi{enc.hid[0], hid_ld(0), Lx.b, nullptr, 0, 1, 1.f};
-        if (tc::CHAIN_RELU_BITS && h->chain_on && (h->debug_flags & DBG_RELU_BITS)) { epi.relu_bits = enc.bits[0]; epi.ld_bits = round_up(B, 32); }
+        if (tc::CHAIN_RELU_BITS && h->chain_on && h->row_jobs && !(h->debug_flags & DBG_NO_RELU_BITS)) { epi.relu_bits = enc.bits[0]; epi.ld_bits = round_up(B, 32); }
         GM_TRY(lin_fwd<A>(h, x_act, Dp, B, Lx, epi, st, y_act, Kp, &Ly));
         h->relu_bits_valid[enc.hid[0]] = epi.relu_bits != nullptr && h->last_gemm_chained;
       }

@@ -42,11 +42,10 @@ template <> struct epi_kind<EpiBCE<bf16>> { static constexpr int value = EK_BCE;
 template <> struct epi_kind<EpiReluMask<bf16, bf16>> { static constexpr int value = EK_RELUMASK; };
 template <> struct epi_kind<EpiAtomicAdd> { static constexpr int value = EK_ATOMIC; };
 
-#ifdef GMVAE_RELU_BITS
-constexpr bool CHAIN_RELU_BITS = true;    // experiment: 1-bit ReLU masks between forward and backward jobs (1 % slower, see engine.cu)
-#else
-constexpr bool CHAIN_RELU_BITS = false;
-#endif
+// 1-bit ReLU masks between the forward and the backward jobs of a layer (written by the forward epilogue, one coalesced 128-byte line per
+// warp and 32 columns; read by the data-gradient epilogue with one 4-byte load per row issued ahead of the accumulator) instead of a
+// TMA load of the bf16 activation box in the epilogue's critical path.  Switched per step by the host (engine.cu, DBG_NO_RELU_BITS).
+constexpr bool CHAIN_RELU_BITS = true;
 constexpr int CHAIN_MAX_JOBS = 40;     // a whole forward + backward pass of the 3-MLP model is 33 jobs
 constexpr int CHAIN_MAX_MAPS = 112;    // tensor maps of all jobs (operands, TMA-stored outputs, ReLU-mask sources)
 constexpr int CHAIN_MAX_DEPS = 4;
