@@ -362,7 +362,7 @@ def run_gpu_arm(args, w):
     peak_tf, peak_hbm, peak_src = measured_peaks()
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/), per launch
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp)).get(f"{args.workload}:{args.objective}:{args.precision}")
         if tj and world == 1 and B == w["batch"]:
