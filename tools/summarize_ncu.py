@@ -39,6 +39,8 @@ def launches(src, dst, cmd):
         items.append((short_name(d["name"]), d["grid"], t, tp))
     starts = [i for i, it in enumerate(items) if it[0].startswith(("convert_x", "prologue_kernel"))]
     step = items[starts[-2]:starts[-1]] if len(starts) >= 2 else items
+    foreign = [i for i in step if i[0].startswith("at::")]           # bench.py's untimed L2 flush between steps (torch add_)
+    step = [i for i in step if not i[0].startswith("at::")]
     tot = sum(i[2] for i in step)
     agg = collections.OrderedDict()
     for n, g, t, tp in step:
@@ -48,7 +50,8 @@ def launches(src, dst, cmd):
         f.write(f"# ncu launch list of one training step\n\nCommand: `{cmd}`\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active... --clock-control none`; per-launch times are cold-cache and "
                 "serialised, so the SHARE of the step is what is comparable with the CUDA-event numbers of bench.py, not the absolute.\n\n")
-        f.write(f"One step = {len(step)} launches, {tot:.1f} us summed under ncu.\n\n## By kernel\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
+        f.write(f"One step = {len(step)} launches, {tot:.1f} us summed under ncu"
+                + (f" ({len(foreign)} torch launch(es) between the steps -- bench.py's untimed L2 flush -- left out)" if foreign else "") + ".\n\n## By kernel\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |\n")
         f.write("\n## In launch order\n\n| # | kernel | grid | us | tensor pipe active % |\n|---:|---|---|---:|---:|\n")
