@@ -55,6 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-I", inc, "-I", os.path.join(HERE, "..", "include")]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("GMVAE_NVCC_FLAGS", "").split()      # experiments (e.g. -DGMVAE_PAIR_STAGES=4)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-o", LIB, "-L", libdir, "-l:libnccl.so.2", "-Xlinker", "-rpath", "-Xlinker", libdir, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -368,7 +368,7 @@ struct EpiStore {
 
   template <int NV>
   __device__ __forceinline__ Pre<NV> prefetch(int m, int n0, int nvalid, bool valid, const EpiCtx&) const {
-    Pre<NV> p;
+    Pre<NV> p = {};
     if constexpr (NV < 16) {
       if (bias) {
         load_frag<NV>(bias + n0, p.b, nvalid);

@@ -52,9 +52,12 @@ constexpr int CHAIN_MAX_DEPS = 4;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 // CTA-pair mode (cta_group::2, see gemm_tc.cuh): a stage holds this CTA's 128 rows of A and HALF of the B tile's columns
-constexpr int CHAIN_STAGES_PAIR = 6;
+#ifndef GMVAE_PAIR_STAGES
+#define GMVAE_PAIR_STAGES 6
+#endif
+constexpr int CHAIN_STAGES_PAIR = GMVAE_PAIR_STAGES;
 constexpr int CHAIN_STAGE_BYTES_PAIR = A_STAGE_BYTES + 128 * BLOCK_K * 2;   // 32 KB
-static_assert(CHAIN_STAGES_PAIR * CHAIN_STAGE_BYTES_PAIR == CHAIN_STAGES * CHAIN_STAGE_BYTES, "both modes use the same ring area");
+static_assert(CHAIN_STAGES_PAIR * CHAIN_STAGE_BYTES_PAIR <= CHAIN_STAGES * CHAIN_STAGE_BYTES, "both modes use the same ring area");
 constexpr int CHAIN_EPI_BYTES = 128;
 constexpr int CHAIN_EPI2_BYTES = 64;
 constexpr int CHAIN_PATCH_BYTES = 2048;   // per epilogue warp: 32 rows x 64 B, the box of one TMA store (SWIZZLE_64B like the tensor map)

@@ -76,6 +76,7 @@ class Engine:
         self._keep = []          # tensors referenced by in-flight / captured work
         self._graph_ready = False
         self.world_size, self.rank = 1, 0
+        self.peer_attached = False
         if seed is not None:
             _lib.check(self.lib.gmvae_set_seed(self._h, int(seed) & (2 ** 64 - 1)))
         if init:
@@ -346,17 +347,39 @@ class Engine:
         if os.environ.get("GMVAE_DP_PEER", "1") != "0":
             self.attach_peers()
 
-    def attach_peers(self):
+    def attach_peers(self) -> bool:
         """The exchange step over NVLink peer memory, fused with Adam (csrc/peer.cuh), in place of the NCCL all-reduce (default
         under data parallelism; GMVAE_DP_PEER=0 keeps NCCL).  Every rank exports its symmetric region, the cudaIpc handles travel
         through torch.distributed, and a barrier separates attaching from the first step.  The gradient buffer moves into the
-        region: `self.grads` is re-pointed at it (zero-copy view of library-owned memory)."""
+        region: `self.grads` is re-pointed at it (zero-copy view of library-owned memory).  The ranks agree after each phase on
+        whether it worked everywhere; if the regions cannot be exported (no P2P / IPC) every rank stays with NCCL and this returns
+        False."""
+        import warnings
         import torch.distributed as dist
+
+        def everywhere(ok: bool) -> bool:
+            oks = [None] * self.world_size
+            dist.all_gather_object(oks, bool(ok))
+            return all(oks)
+
         buf = C.create_string_buffer(64)
-        _lib.check(self.lib.gmvae_peer_export(self._h, self.world_size, self.rank, buf), "gmvae_peer_export")
+        err = None
+        try:
+            _lib.check(self.lib.gmvae_peer_export(self._h, self.world_size, self.rank, buf), "gmvae_peer_export")
+        except RuntimeError as e:
+            err = e
+        if not everywhere(err is None):
+            warnings.warn(f"peer-memory gradient exchange unavailable ({err or 'another rank could not export its region'}); using the NCCL all-reduce")
+            return False
         handles = [None] * self.world_size
         dist.all_gather_object(handles, bytes(buf.raw))
-        _lib.check(self.lib.gmvae_peer_attach(self._h, b"".join(handles)), "gmvae_peer_attach")
+        try:
+            _lib.check(self.lib.gmvae_peer_attach(self._h, b"".join(handles)), "gmvae_peer_attach")
+        except RuntimeError as e:
+            err = e
+        if not everywhere(err is None):
+            # a rank that did attach has already moved its gradient buffer: there is no common fallback left
+            raise RuntimeError(f"the peer-memory exchange could be attached on some ranks only ({err}); run with GMVAE_DP_PEER=0")
         ptr = self.lib.gmvae_peer_grads(self._h)
 
         class _Raw:                                              # torch.as_tensor understands the CUDA array interface: no copy
@@ -365,7 +388,9 @@ class Engine:
             self._grads_bound = self.grads
             self.grads = torch.as_tensor(_Raw(), device=self.device)
         self._graph_ready = False
+        self.peer_attached = True
         dist.barrier()
+        return True
 
     PROFILE_CLASSES = ["tc_gemm_fwd_dgrad", "tc_gemm_wgrad", "simt_gemm", "heads", "bias_grad", "adam_refresh", "misc", "comm"]
 
