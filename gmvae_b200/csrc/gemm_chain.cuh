@@ -53,7 +53,7 @@ constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 // CTA-pair mode (cta_group::2, see gemm_tc.cuh): a stage holds this CTA's 128 rows of A and HALF of the B tile's columns
 #ifndef GMVAE_PAIR_STAGES
-#define GMVAE_PAIR_STAGES 6
+#define GMVAE_PAIR_STAGES 6       // experiment hook (GMVAE_NVCC_FLAGS=-DGMVAE_PAIR_STAGES=3: +7 % per k-block -- the ring depth does not pace the main loop)
 #endif
 constexpr int CHAIN_STAGES_PAIR = GMVAE_PAIR_STAGES;
 constexpr int CHAIN_STAGE_BYTES_PAIR = A_STAGE_BYTES + 128 * BLOCK_K * 2;   // 32 KB
@@ -358,6 +358,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
   uint64_t* const op_bar = S.op_bar + e;
   const int gw = J.gw;
   int cs_n0 = -1;
+  int staged_n0 = -1;                                     // n-tile whose bias sits in the staging buffer
   float fuse_acc = 0.f;                                  // fused y head: sum p log p (forward) of this thread's rows
   bool fuse_bwd = false;
   if constexpr (KIND == EK_STORE_F32) fuse_bwd = J.fuse == EK_ROWS_Y_BWD;   // its bias-gradient sums use the CTA accumulator
@@ -377,15 +378,17 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
     const int mrow0 = m0 + quad * 32;
     const int m = mrow0 + lane;
     float* sbias = S.sbias_all;
-    // bias of this tile's columns, staged once per tile (single buffer: every warp has finished the previous tile's reads)
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-    {
+    // bias of this tile's columns, staged when the CTA moves to another n-tile (with an even number of walkers and n-tiles a CTA
+    // keeps its n-tile through a whole job: the two block-wide barriers are then paid once per job, not once per tile)
+    if (n0 != staged_n0) {                                  // uniform over the epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // (every warp has finished the previous tile's reads)
       const uint32_t sb = smem_addr(sbias);
       float shift = 0.f;
       if constexpr (KIND == EK_BCE) shift = epi.gen_bias;     // logits = MLP(z) + bias_init (base.py:135)
       for (int i = et; i < BN; i += EPI_WARPS * 32) sts32f(sb + 4 * i, ((bias && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f) + shift);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      staged_n0 = n0;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     if (cs_dst && cs_n0 != n0) {
       if (cs_n0 >= 0) {
         cs_flush();
@@ -902,11 +905,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   griddep_launch();
 
   if (warp == 0) {
-    {
-      // ===== TMA producer (one warp) =====
-      // The loads of a stage -- A (1 box, or 2 slabs when MN-major) and B (1 box, or up to 4 slabs) -- are issued by as many LANES
-      // in ONE instruction; lane 0 alone does the waiting and the barrier bookkeeping.  A single thread issuing them one after
-      // the other was what paced the main loop (measured: ~0.25 us per k-block + ~0.07 us per TMA instruction, whatever the bytes).
+    if (lane == 0) {
+      // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
       int pit = 0;
       for (int j = 0; j < p.njobs; ++j) {
@@ -918,11 +918,6 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         const int b_slabs = PAIR ? (bhalf + 63) / 64 : BN / 64;
         const uint32_t b_bytes = PAIR ? (uint32_t)(J.b_mn ? b_slabs * (BLOCK_K * 128) : bhalf * BLOCK_K * 2) : (uint32_t)(BN * BLOCK_K * 2);
         const uint32_t tx_bytes = (PAIR ? 2u : 1u) * ((uint32_t)A_STAGE_BYTES + b_bytes);    // pair: both CTAs' loads land on the leader's barrier
-        // this lane's load of a stage: lanes [0, n_a) the A pieces, [n_a, n_a + n_b) the B pieces
-        const int n_a = J.a_mn ? BLOCK_M / 64 : 1, n_b = J.b_mn ? b_slabs : 1;
-        const bool my_a = lane < n_a, my_b = !my_a && lane < n_a + n_b;
-        const int piece = my_a ? lane : lane - n_a;
-        const uint32_t my_off = my_a ? (uint32_t)(piece * (BLOCK_K * 128)) : (uint32_t)(A_STAGE_BYTES + piece * (BLOCK_K * 128));
         const int first = ((c - J.tile_base) % G + G) % G;
         for (int l = first; l < J.total_tiles; l += G, ++pit) {
           int z, mb, n0;
@@ -932,51 +927,54 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
           const int n_eff = min(BN, (J.N - n0 + 15) & ~15);
           const int nb = PAIR ? n0 + rank * (n_eff >> 1) : n0;  // first B column this CTA loads
           const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
-          const bool tr = trace && pit < 64 && lane == 0;
+          const bool tr = trace && pit < 64;
           if (tr) trace[16 * pit + 0] = clock64();
           unsigned long long js_t0 = 0;
-          if (p.jobstat && lane == 0) js_t0 = gtimer();
+          if (p.jobstat) js_t0 = gtimer();
           if (J.ndeps > 0) {
-            if (lane == 0) {
-              for (int d = 0; d < J.ndeps; ++d) {
-                const ChainDep& D = J.deps[d];
-                if (D.seg2) continue;
-                if (!D.by_k) {
-                  if (real) wait_counter(p.counters + D.base + mb, D.target);
-                } else {
-                  const int lo = (kb_begin * BLOCK_K) / BLOCK_M, hi = min(D.nblocks - 1, (kb_end * BLOCK_K - 1) / BLOCK_M);
-                  for (int b = lo; b <= hi; ++b) wait_counter(p.counters + D.base + b, D.target);
-                }
+            for (int d = 0; d < J.ndeps; ++d) {
+              const ChainDep& D = J.deps[d];
+              if (D.seg2) continue;
+              if (!D.by_k) {
+                if (real) wait_counter(p.counters + D.base + mb, D.target);
+              } else {
+                const int lo = (kb_begin * BLOCK_K) / BLOCK_M, hi = min(D.nblocks - 1, (kb_end * BLOCK_K - 1) / BLOCK_M);
+                for (int b = lo; b <= hi; ++b) wait_counter(p.counters + D.base + b, D.target);
               }
             }
-            __syncwarp();
-            fence_proxy_async_global();                       // (every issuing lane: the waited-for rows precede its bulk loads)
+            fence_proxy_async_global();
           }
           if (tr) trace[16 * pit + 1] = clock64();
-          if (p.jobstat && lane == 0) { atomicMin(p.jobstat + 8 * j + 0, js_t0); atomicAdd(p.jobstat + 8 * j + 2, gtimer() - js_t0); }
-          // coordinates of this lane's piece that do not change along K
-          const int my_c_mn = my_a ? (J.a_mn ? m0 + piece * 64 : m0) : (J.b_mn ? nb + piece * 64 : nb);
-          const bool my_mn = my_a ? (J.a_mn != 0) : (J.b_mn != 0);
+          if (p.jobstat) { atomicMin(p.jobstat + 8 * j + 0, js_t0); atomicAdd(p.jobstat + 8 * j + 2, gtimer() - js_t0); }
           for (int kb = kb_begin; kb < kb_end; ++kb) {
             if (kb == kb1 && J.ndeps > 0) {
               // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
               bool any = false;
               for (int d = 0; d < J.ndeps; ++d)
-                if (J.deps[d].seg2) { if (real && lane == 0) wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
-              if (any) { __syncwarp(); fence_proxy_async_global(); }
+                if (J.deps[d].seg2) { if (real) wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
+              if (any) fence_proxy_async_global();
             }
-            if (lane == 0) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const bool seg2 = kb >= kb1;
+            const CUtensorMap* ta = &p.maps[seg2 ? J.a2 : J.a1];
+            const CUtensorMap* tb = &p.maps[seg2 ? J.b2 : J.b1];
+            const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+              if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1); else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+            };
+            if (J.a_mn) {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i) ld(ta, sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+            } else {
+              ld(ta, sa, k_elem, m0);
             }
-            __syncwarp();
-            if (my_a || my_b) {
-              const bool seg2 = kb >= kb1;
-              const CUtensorMap* tm = &p.maps[my_a ? (seg2 ? J.a2 : J.a1) : (seg2 ? J.b2 : J.b1)];
-              const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
-              uint8_t* dst = smem + stage * STAGE_BYTES + my_off;
-              const int c0 = my_mn ? my_c_mn : k_elem, c1 = my_mn ? k_elem : my_c_mn;
-              if (PAIR) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1); else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
+            if (J.b_mn) {
+              for (int i = 0; i < b_slabs; ++i) ld(tb, sb + i * (BLOCK_K * 128), nb + i * 64, k_elem);
+            } else {
+              ld(tb, sb, k_elem, nb);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
