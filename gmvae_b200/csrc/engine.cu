@@ -431,6 +431,7 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain.counters = h->chain_counters;
   h->chain.trace = (h->chain_trace && h->chain_launch_idx < 8) ? h->chain_trace + (size_t)h->chain_launch_idx * 64 * 16 : nullptr;
   h->chain.trace_cta = h->chain_trace_cta;
+  { static const int abl = getenv("GMVAE_CHAIN_ABL") ? atoi(getenv("GMVAE_CHAIN_ABL")) : 0; h->chain.abl = abl; }
   h->chain.jobstat = (h->chain_jobstat && h->chain_launch_idx == 0) ? h->chain_jobstat : nullptr;
   if (h->chain.jobstat) {
     h->chain_jobdesc.clear();
@@ -466,7 +467,7 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   if (h->chain.njobs <= tc::CHAIN_SMALL_JOBS && h->chain.nmaps <= tc::CHAIN_SMALL_MAPS) {
     static tc::ChainParamsSmall small;                      // the launch copies it
     small.njobs = h->chain.njobs; small.nmaps = h->chain.nmaps; small.counters = h->chain.counters;
-    small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta; small.jobstat = h->chain.jobstat;
+    small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta; small.jobstat = h->chain.jobstat; small.abl = h->chain.abl;
     memcpy(small.maps, h->chain.maps, sizeof(CUtensorMap) * h->chain.nmaps);
     memcpy(small.jobs, h->chain.jobs, sizeof(tc::ChainJob) * h->chain.njobs);
     GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall, false>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));

@@ -95,6 +95,7 @@ struct ChainParamsT {
   int* counters;
   long long* trace;    // test hook: clock64 stamps of CTA `trace_cta`, 16 per processed tile (null in production)
   int trace_cta;
+  int abl;             // timing-only ablations (builds with -DGMVAE_CHAIN_ABL; results are garbage): 1 epilogues skip their work, 2 no TMA loads, 4 no MMAs
   unsigned long long* jobstat;   // test hook: 8 counters per job over ALL CTAs (globaltimer ns): [0] first tile start, [1] last tile end,
                                  // [2] producer dependency wait, [3] MMA issue->commit, [4] epilogue rows, [5] epilogue wait for the
                                  // accumulator, [6] tiles, [7] MMA wait for a free accumulator (null in production)
@@ -338,7 +339,7 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
 template <class Epi, int KIND, bool PAIR>
 __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUtensorMap* maps, int* counters, const ChainShared& S, int& it,
                                                    uint32_t& op_phase, int warp, int lane, long long* trace, int jidx,
-                                                   unsigned long long* jobstat = nullptr) {
+                                                   unsigned long long* jobstat = nullptr, int abl = 0) {
   constexpr int CW = 16;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
   // GEMM tiles are dealt round-robin to the CTAs -- in pair mode to the CTA pairs, both CTAs of a pair walking the same pair tiles
@@ -397,6 +398,18 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
       cs_n0 = n0;
     }
     const bool mvalid = m < M;
+#ifdef GMVAE_CHAIN_ABL
+    if (abl & 1) {
+      mbar_wait(&S.tmem_full_bar[it & 1], (it >> 1) & 1);
+      tc_fence_after(); tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&S.tmem_empty_bar[it & 1]); else mbar_arrive(&S.tmem_empty_bar[it & 1]);
+        if (J.sig_base >= 0) { __threadfence(); atomicAdd(counters + J.sig_base + mb, 1); }
+      }
+      continue;
+    }
+#endif
     const bool tr = trace && e == 0 && lane == 0 && it < 64;
     if (tr) { trace[16 * it + 6] = clock64(); trace[16 * it + 15] = jidx; trace[16 * it + 14] = l; }
     const bool js = jobstat && e == 0 && lane == 0;
@@ -961,6 +974,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
             const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
+#ifdef GMVAE_CHAIN_ABL
+            if (p.abl & 2) {
+              if (!PAIR || rank == 0) mbar_arrive(&full_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+#endif
             if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
             auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
               if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1); else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
@@ -1020,6 +1040,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
             const uint64_t adesc = make_smem_desc_rt(sa, a_mn);
             const uint64_t bdesc = make_smem_desc_rt(sa + A_STAGE_BYTES, b_mn);
+#ifdef GMVAE_CHAIN_ABL
+            if (!(p.abl & 4))
+#endif
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               if (PAIR) umma_bf16_pair(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
@@ -1042,11 +1065,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
 #ifndef GMVAE_NO_ROWS
         case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
         case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
