@@ -134,6 +134,10 @@ enum { DBG_NO_TC = 1, DBG_NO_TC_WGRAD = 2, DBG_NO_TWO_SEG = 4, DBG_SYNC_EACH = 8
                               pass is ONE launch).  Default: on for batches of >= 32 row blocks.  Measured: cfg4 (128 blocks) 0.415 ms
                               vs 0.423 ms with the heads as 4 kernels between 5 chained launches; batch 100: 0.240 vs 0.199 ms. */,
        DBG_NO_PAIR = 65536 /* run the one-launch plan on single CTAs (tcgen05 cta_group::1, 128 x 256 tiles) instead of CTA pairs */,
+       DBG_NO_QUAD = 131072 /* CTA pairs without the 4-CTA clusters that share the A rows of a row block's two n-tiles by TMA multicast */,
+       DBG_WG_LATE = 262144 /* one-launch plan: every weight-gradient job after the data-gradient chain instead of interleaved with it
+                                (measured: 0.378 vs 0.350 ms at cfg4 -- the chain alone leaves the SMs 80 % idle) */,
+       DBG_NO_PARTITION = 524288 /* backward pass: chain and weight-gradient jobs on the same CTA pairs (no walker partition) */,
        DBG_NO_RELU_BITS = 2048 /* one-launch plan: read the ReLU mask of the backward pass from the bf16 activation (TMA load in the epilogue)
                                   instead of the 1-bit masks the forward epilogues write */ };
 // kernel classes of the per-launch profile (gmvae_profile_read)
@@ -195,13 +199,22 @@ struct gmvae_handle {
   struct ChainWriter { const char* lo; const char* hi; int job; };
   std::vector<ChainWriter> chain_writers;
   int chain_tiles = 0;
+  int max_quads = 0;
   int* chain_counters = nullptr; int chain_counter_cap = 0, chain_counter_next = 0;
   long long* chain_trace = nullptr; int chain_trace_cta = 0, chain_launch_idx = 0;   // test hook (gmvae_debug_chain_trace)
   unsigned long long* chain_jobstat = nullptr;     // test hook (gmvae_debug_chain_jobstat): 8 counters per job of the step's first chained launch
   std::vector<int> chain_jobdesc;                  // 8 ints per job of that launch: kind, M, N, k-blocks, tiles, splits, block_n, ndeps
   bool chain_flush_after = false;
   bool row_jobs = false;                          // this step: distribution heads run as row jobs of the chained kernel
+  bool quad_opt_in = false;                       // GMVAE_CHAIN_QUAD=1 (read at gmvae_create)
+  int chain_split_opt = 0;                        // GMVAE_CHAIN_SPLIT=<pairs on the dependent chain> (0: no walker partition)
   int wide_bn = 0;                                // tile width of jobs with more than 128 output columns (0: 256); GMVAE_CHAIN_BN
+  std::vector<std::function<int()>>* wg_late = nullptr;   // one-launch plan: every weight-gradient GEMM is recorded after the data-gradient chain
+  // walker partition of the backward pass (ChainJob::wfirst / wcount): 0 = every walker, 1 = the dependent chain (data gradients, heads),
+  // 2 = weight gradients.  part_tiles: tiles recorded per class (the round-robin phase of the next job of that class).
+  int cur_part = 0, part_chain_walkers = 0, part_walkers = 0, part_tiles[3] = {0, 0, 0};
+  bool part_on = false, part_last_mlp = false, part_tail = false;
+  bool chain_quad = false;                        // ... in clusters of two pairs sharing A rows by multicast (gemm_chain.cuh, CL = 4)
   bool chain_pair = false;                        // this step: the chained kernel runs on CTA pairs (cta_group::2, 256-row tiles)
   // a y head to be fused into the epilogue of the next thin fp32 GEMM job (set by the step driver, consumed by chain_add)
   struct FuseReq { int kind = 0; unsigned char prm[tc::CHAIN_EPI2_BYTES]; std::vector<std::pair<const void*, size_t>> writes; bool consumed = false; };
@@ -417,6 +430,26 @@ static bool tc_ok_dgrad(const gmvae_handle* h, const TD* dY, int64_t ldy, const 
 // ============================================================================ GEMM chains
 // Launches the recorded jobs as one persistent kernel (gemm_chain.cuh).  Must be called before
 // anything else is enqueued on `st` that reads what the jobs write.
+// CTA pairs of the chained kernel the device can co-schedule (every cluster must be resident at once: the row-block waits assume it)
+static int pair_max_clusters(gmvae_handle* h, int* out) {
+  static int max_clusters_by_dev[64] = {};
+  int& max_clusters = max_clusters_by_dev[tc::current_device()];
+  if (max_clusters == 0) {
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(tc::num_sms() & ~1); qc.blockDim = dim3(tc::NUM_THREADS2); qc.dynamicSmemBytes = tc::CHAIN_SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    int n = 0;
+    GM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, tc::gemm_chain_kernel<tc::ChainParams, 2>, &qc));
+    GM_REQUIRE(n >= 1, "the device cannot co-schedule a CTA pair of the chained kernel");
+    max_clusters = n;
+  }
+  *out = max_clusters;
+  return 0;
+}
+
 static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   h->chain_flush_after = false;
   h->last_gemm_chained = false;
@@ -424,8 +457,8 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
   static bool attr_set_by_dev[64] = {};                      // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_by_dev[tc::current_device()];
   if (!attr_set) {
-    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
-    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+    GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParamsSmall, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
     attr_set = true;
   }
   h->chain.counters = h->chain_counters;
@@ -442,25 +475,18 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
     }
   }
   h->chain_launch_idx++;
-  if (h->chain_pair) {
+  if (h->chain_quad) {
+    // clusters of two CTA pairs; chain_tiles counts double tiles
+    const int clusters = std::max(1, std::min(h->chain_tiles, h->max_quads));
+    GM_CHECK_CUDA(launch_k_cluster(tc::gemm_chain_kernel<tc::ChainParams, 4>, dim3(4 * clusters), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, 4,
+                           h->chain));
+  } else if (h->chain_pair) {
     // CTA pairs: clusters of 2 (the two SMs of a TPC); chain_tiles counts pair tiles.  Every cluster must be resident at once
     // (the row-block waits assume it), so the grid is capped by what the device can co-schedule.
-    static int max_clusters_by_dev[64] = {};
-    int& max_clusters = max_clusters_by_dev[tc::current_device()];
-    if (max_clusters == 0) {
-      GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
-      cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(tc::num_sms() & ~1); qc.blockDim = dim3(tc::NUM_THREADS2); qc.dynamicSmemBytes = tc::CHAIN_SMEM_BYTES;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      qc.attrs = qa; qc.numAttrs = 1;
-      int n = 0;
-      GM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, tc::gemm_chain_kernel<tc::ChainParams, true>, &qc));
-      GM_REQUIRE(n >= 1, "the device cannot co-schedule a CTA pair of the chained kernel");
-      max_clusters = n;
-    }
+    int max_clusters = 0;
+    GM_TRY(pair_max_clusters(h, &max_clusters));
     const int pairs = std::max(1, std::min(std::min(h->chain_tiles, tc::num_sms() / 2), max_clusters));
-    GM_CHECK_CUDA(launch_k_cluster(tc::gemm_chain_kernel<tc::ChainParams, true>, dim3(2 * pairs), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, 2,
+    GM_CHECK_CUDA(launch_k_cluster(tc::gemm_chain_kernel<tc::ChainParams, 2>, dim3(2 * pairs), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, 2,
                            h->chain));
   } else {
   const int grid = std::min(h->chain_tiles, tc::num_sms());
@@ -470,9 +496,9 @@ static int chain_flush(gmvae_handle* h, cudaStream_t st) {
     small.trace = h->chain.trace; small.trace_cta = h->chain.trace_cta; small.jobstat = h->chain.jobstat; small.abl = h->chain.abl;
     memcpy(small.maps, h->chain.maps, sizeof(CUtensorMap) * h->chain.nmaps);
     memcpy(small.jobs, h->chain.jobs, sizeof(tc::ChainJob) * h->chain.njobs);
-    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall, false>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParamsSmall, 1>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, small));
   } else {
-    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParams, false>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
+    GM_CHECK_CUDA(launch_k(tc::gemm_chain_kernel<tc::ChainParams, 1>, dim3(grid), dim3(tc::NUM_THREADS2), (size_t)tc::CHAIN_SMEM_BYTES, st, true, h->chain));
   }
   }
   h->chain.njobs = 0; h->chain.nmaps = 0; h->chain_tiles = 0; h->chain_writers.clear();
@@ -515,7 +541,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
                      int M, int N, int block_n, bool a_mn, bool b_mn, int split_k, const Epi& epi, cudaStream_t st) {
   static_assert(tc::epi_kind<Epi>::value != tc::EK_NONE, "epilogue not supported by the chained kernel");
   static_assert(sizeof(Epi) <= tc::CHAIN_EPI_BYTES, "epilogue parameters do not fit the job record");
-  const bool pair = h->chain_pair;
+  const bool pair = h->chain_pair, quad = h->chain_quad;
   const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M, tiles_n = (N + block_n - 1) / block_n;
   const int tiles_m_walk = pair ? (tiles_m + 1) / 2 : tiles_m;          // pair mode: tiles of 256 rows, one row block per CTA of the pair
   // ---- dependencies
@@ -556,11 +582,12 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   };
   const int b_box_rows = pair ? block_n / 2 : block_n;                 // K-major B: a CTA of a pair loads half of the tile's rows
   GM_REQUIRE(!pair || block_n % 16 == 0, "pair tiles need a tile width that is a multiple of 16");
-  GM_TRY(mk(&J.a1, A1, a_mn, tc::BLOCK_M));
+  const int a_box_rows = quad ? 64 : tc::BLOCK_M;                      // quad mode loads A in halves of 64 rows
+  GM_TRY(mk(&J.a1, A1, a_mn, a_box_rows));
   GM_TRY(mk(&J.b1, B1, b_mn, b_box_rows));
   J.kb1 = (A1.k + tc::BLOCK_K - 1) / tc::BLOCK_K; J.kb2 = 0;
   if (A2 && B2) {
-    GM_TRY(mk(&J.a2, *A2, a_mn, tc::BLOCK_M));
+    GM_TRY(mk(&J.a2, *A2, a_mn, a_box_rows));
     GM_TRY(mk(&J.b2, *B2, b_mn, b_box_rows));
     J.kb2 = (A2->k + tc::BLOCK_K - 1) / tc::BLOCK_K;
   } else {
@@ -573,6 +600,16 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   J.M = M; J.N = N; J.kb_per_split = per; J.num_splits = split_k;
   J.block_n = block_n; J.a_mn = a_mn ? 1 : 0; J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
   J.tiles_n = tiles_n; J.tiles_mn = tiles_m_walk * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
+  J.tiles_mn2 = (J.tiles_mn + 1) / 2;
+  J.walk_total = quad ? J.tiles_mn2 * split_k : J.total_tiles;
+  {
+    const int part = h->part_on ? h->cur_part : 0;
+    J.wfirst = part == 2 ? h->part_chain_walkers : 0;
+    J.wcount = part == 1 ? h->part_chain_walkers : part == 2 ? h->part_walkers - h->part_chain_walkers : 0;
+    J.tile_base = part == 0 ? h->chain_tiles : h->part_tiles[part];
+    h->part_tiles[part] += J.walk_total;
+  }
+  J.share = (quad && tiles_n % 2 == 0) ? 1 : 0;
   J.ndeps = ndeps; J.epi_dep = epi_dep;
   J.rot = (tiles_n > 1 && N % block_n != 0 && !a_mn) ? 1 : 0;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
@@ -580,7 +617,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   writer_range(epi, M, lo, hi);
   J.sig_base = -1;
   if (lo) {
-    const int ncount = pair ? 2 * tiles_m_walk : tiles_m;               // (a pair's phantom half signals a counter nobody waits for)
+    const int ncount = pair ? 2 * tiles_m_walk + (quad ? 2 : 0) : tiles_m;   // (phantom halves / phantom pair tiles signal counters nobody waits for)
     if (h->chain_counter_next + ncount <= h->chain_counter_cap) {
       J.sig_base = h->chain_counter_next; h->chain_counter_next += ncount;
     } else {
@@ -610,7 +647,7 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
       if (w.first) h->chain_writers.push_back({reinterpret_cast<const char*>(w.first), reinterpret_cast<const char*>(w.first) + w.second, h->chain.njobs});
     h->fuse_next.consumed = true;
   }
-  h->chain_tiles += J.total_tiles;
+  h->chain_tiles += J.walk_total;
   h->chain.njobs++;
   h->last_gemm_chained = true;
   if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
@@ -644,7 +681,15 @@ static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::i
   memset(&J, 0, sizeof(J));
   J.M = M; J.N = 0; J.kind = kind; J.num_splits = 1;
   // row tiles are dealt to single CTAs also in pair mode, where chain_tiles counts pair tiles
-  J.tiles_n = sub; J.tiles_mn = tiles_m * sub; J.total_tiles = tiles_m * sub; J.tile_base = h->chain_pair ? 2 * h->chain_tiles : h->chain_tiles;
+  J.tiles_n = sub; J.tiles_mn = tiles_m * sub; J.total_tiles = tiles_m * sub; J.tile_base = (h->chain_quad ? 4 : h->chain_pair ? 2 : 1) * h->chain_tiles;
+  {
+    const int cl = h->chain_quad ? 4 : h->chain_pair ? 2 : 1;
+    const int part = h->part_on ? h->cur_part : 0;
+    J.wfirst = part == 2 ? h->part_chain_walkers : 0;
+    J.wcount = part == 1 ? h->part_chain_walkers : part == 2 ? h->part_walkers - h->part_chain_walkers : 0;
+    if (part != 0) J.tile_base = cl * h->part_tiles[part];
+    h->part_tiles[part] += (tiles_m * sub + cl - 1) / cl;
+  }
   J.ndeps = ndeps; J.epi_dep = -1;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
   J.sig_base = -1;
@@ -656,7 +701,7 @@ static int chain_add_rows(gmvae_handle* h, int kind, const P& prm, int M, std::i
   for (const auto& w : writes)
     if (w.first) h->chain_writers.push_back({reinterpret_cast<const char*>(w.first), reinterpret_cast<const char*>(w.first) + w.second, h->chain.njobs});
   memcpy(J.epi, &prm, sizeof(P));
-  h->chain_tiles += h->chain_pair ? (J.total_tiles + 1) / 2 : J.total_tiles;
+  { const int cl = h->chain_quad ? 4 : h->chain_pair ? 2 : 1; h->chain_tiles += (J.total_tiles + cl - 1) / cl; }
   h->chain.njobs++;
   if (h->chain_flush_after) GM_TRY(chain_flush(h, st));
   return 0;
@@ -757,8 +802,19 @@ static int lin_wgrad(gmvae_handle* h, const TA* A, int64_t lda, const TD* dY, in
       const int kb = (M + tc::BLOCK_K - 1) / tc::BLOCK_K;
       // one wave of persistent CTAs (CTA pairs): split the batch so that tiles * split ~ number of SMs (pairs),
       // keeping at least 4 k-blocks (256 samples) per split
-      int split = std::max(1, std::min(std::max(1, kb / 4), (pair ? tc::num_sms() / 2 : tc::num_sms()) / tiles));
-      if (h->chain_on) return chain_add(h, a, b, nullptr, nullptr, L.in, L.out, bn, true, true, split, epi, st);
+      const bool quad = pair && h->chain_quad;       // walkers: 4-CTA clusters taking double tiles
+      const int walkers = quad ? h->max_quads : pair ? tc::num_sms() / 2 : tc::num_sms(), units = quad ? (tiles + 1) / 2 : tiles;
+      // (with the walker partition a job is two rounds of the weight-gradient pairs: same tiles, same split)
+      // (measured at cfg4, tiles x splits as a multiple of the walkers: 0.34 / 0.5 / 0.75 / 1 / 2 / 3 / 4 -> 0.386 / 0.356 / 0.348 / 0.347 / 0.376 /
+      // 0.395 / 0.419 ms: shorter tiles pay the reduce-add epilogue more often, longer ones leave pairs without a tile)
+      int split = std::max(1, std::min(std::max(1, kb / 4), walkers / units));
+      if (h->chain_on) {
+        const int saved_part = h->cur_part;
+        if (saved_part == 1) h->cur_part = h->part_tail ? 0 : 2;      // weight gradients: their own walkers (the tail: everybody)
+        const int r = chain_add(h, a, b, nullptr, nullptr, L.in, L.out, bn, true, true, split, epi, st);
+        h->cur_part = saved_part;
+        return r;
+      }
       GM_TRY(chain_flush(h, st));
       int r = bn == 64    ? tc::launch_gemm_tc<64, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
               : bn == 128 ? tc::launch_gemm_tc<128, true, true, EpiAtomicAdd>(a, b, nullptr, nullptr, L.in, L.out, split, epi, st)
@@ -865,6 +921,7 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
       if (top) GM_TRY((lin_dgrad<TD>(h, dOut, ld_dout, M, Lf, epi, st)));
       else GM_TRY((lin_dgrad<A>(h, dA, ldd, M, Lf, epi, st)));
       next_bias_done = cs != nullptr;
+      if (h->part_last_mlp && i == 1) h->part_tail = true;      // that was the last job of the dependent chain
     }
     const bool need_bias = !bias_done;
     const int out_cols = l.out;
@@ -882,7 +939,8 @@ static int mlp_backward(gmvae_handle* h, const Mlp& m, const MlpBufs<A>& b, cons
         return 0;
       };
     }
-    if (defer && i < defer_below) defer->push_back(wg); else GM_TRY(wg());
+    if (h->wg_late) h->wg_late->push_back(wg);
+    else if (defer && i < defer_below) defer->push_back(wg); else GM_TRY(wg());
     bias_done = next_bias_done;
   }
   return 0;
@@ -1040,10 +1098,44 @@ static int forward_backward_impl(gmvae_handle* h, const uint8_t* x_u8, int B, in
   h->row_jobs = h->chain_on && !(h->debug_flags & DBG_NO_ROW_JOBS) && (B >= 32 * tc::BLOCK_M || (h->debug_flags & DBG_ROW_JOBS));
   // CTA pairs (256-row tiles) where the one-launch plan runs: large batches, every SM available
   h->chain_pair = h->row_jobs && !(h->debug_flags & DBG_NO_PAIR) && !(h->comm && h->world > 1 && h->overlap_comm) && tc::g_reserved_sms == 0;
+  h->chain_quad = false;
+  // Measured slower than plain pairs so far (0.379 vs 0.348 ms at cfg4: the two pairs of a cluster advance in lock-step through the
+  // shared ring slots, and the multicast halves the L2 reads of A but not what each SM receives): opt-in, GMVAE_CHAIN_QUAD=1.
+  if (h->chain_pair && h->quad_opt_in && !(h->debug_flags & DBG_NO_QUAD)) {
+    // clusters of 4: how many the device can co-schedule (a GPC with an odd number of TPCs leaves one idle); cached per device
+    static int max_quads_by_dev[64] = {};
+    int& mq = max_quads_by_dev[tc::current_device()];
+    if (mq == 0) {
+      GM_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_chain_kernel<tc::ChainParams, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::CHAIN_SMEM_BYTES));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(tc::num_sms() & ~3); qc.blockDim = dim3(tc::NUM_THREADS2); qc.dynamicSmemBytes = tc::CHAIN_SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 4; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc::gemm_chain_kernel<tc::ChainParams, 4>, &qc) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      mq = n > 0 ? std::min(n, tc::num_sms() / 4) : -1;
+      if (getenv("GMVAE_VERBOSE")) fprintf(stderr, "[gmvae] 4-CTA clusters of the chained kernel co-resident on this device: %d\n", n);
+    }
+    h->max_quads = mq;
+    h->chain_quad = mq >= 28;                    // fewer than 112 of the SMs in clusters: stay with pairs
+  }
+  h->part_on = false; h->cur_part = 0; h->part_tail = false; h->part_last_mlp = false;
+  h->part_tiles[0] = h->part_tiles[1] = h->part_tiles[2] = 0;
+  if (h->chain_pair && !h->chain_quad && !(h->debug_flags & DBG_NO_PARTITION)) {
+    int mc = 0;
+    GM_TRY(pair_max_clusters(h, &mc));
+    const int W = std::min(tc::num_sms() / 2, mc);
+    const int split_env = h->chain_split_opt;
+    // Measured at cfg4: 0.458 / 0.415 / 0.387 / 0.358 / 0.405 ms with 24 / 30 / 37 / 44 / 52 of the 74 pairs on the chain against 0.354 ms
+    // without a partition (the chain's tiles are paced by their epilogues, fewer pairs stretch every stage): off unless asked for.
+    const int x = split_env;
+    if (x >= 4 && W - x >= 4) { h->part_on = true; h->part_walkers = W; h->part_chain_walkers = x; }
+  }
   if (h->chain_on) GM_CHECK_CUDA(cudaMemsetAsync(h->chain_counters, 0, (size_t)h->chain_counter_cap * 4, st));
   int r = forward_backward_body<A>(h, x_u8, B, Bg, eps_in, u_in, st);
   if (r == 0) r = chain_flush(h, st);
-  h->chain_on = false; h->chain_pair = false; h->chain.njobs = 0; h->chain.nmaps = 0;
+  h->chain_on = false; h->chain_pair = false; h->chain_quad = false; h->chain.njobs = 0; h->chain.nmaps = 0;
   return r;
 }
 
@@ -1135,6 +1227,16 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   // gradients only read finished tensors, so in the chained kernel they are placed where that path has bubbles:
   // right after the thin jobs (dz, dy, the heads), whose dependants would otherwise wait out a full tile latency.
   const bool spread = h->chain_on && h->row_jobs && !(h->debug_flags & DBG_NO_SPREAD) && !(h->comm && h->world > 1 && h->overlap_comm);
+  // In-order CTAs cannot step over a weight-gradient tile (28 k-blocks, 9-15 us, and waiting for a whole batch slice of its operands)
+  // to the data-gradient tile behind it: interleaved, every stage of the dependent chain paid for one (20.8 us per stage against 9.3
+  // in the forward pass).  In the one-launch plan all weight gradients therefore follow the chain, where nothing waits for them.
+  std::vector<std::function<int()>> wg_late;
+  struct WgLateGuard { gmvae_handle* h; ~WgLateGuard() { h->wg_late = nullptr; } } wg_late_guard{h};
+  if (spread && (h->debug_flags & DBG_WG_LATE)) h->wg_late = &wg_late;
+  // Walker partition: from here on the chain jobs are dealt to the first part_chain_walkers CTA pairs and the weight-gradient jobs
+  // to the others (the tail after the last data gradient to everybody again).
+  struct PartGuard { gmvae_handle* h; ~PartGuard() { h->cur_part = 0; h->part_tail = false; h->part_last_mlp = false; } } part_guard{h};
+  if (h->part_on && spread && !h->wg_late) h->cur_part = 1;
   std::vector<std::function<int()>> wg_dec;          // weight gradients of the two lowest decoder layers
   GM_TRY((mlp_backward<A, A>(h, h->decoder, dec, z_act, Zp, Z, dlogits_x, Dp, B, st, dec_bias_fused, 0, spread ? &wg_dec : nullptr,
                              std::min(2, nl - 1))));
@@ -1191,6 +1293,7 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
   }
   for (; wg_dec_next < wg_dec.size(); ++wg_dec_next) GM_TRY(wg_dec[wg_dec_next]());   // filler between the z head and the encoder's data gradients
   std::vector<std::function<int()>> wg_enc;          // weight gradient of the encoder's first layer (x part)
+  if (!gm) { h->part_last_mlp = true; if (h->encoder.layers.size() < 2) h->part_tail = true; }
   GM_TRY((mlp_backward<A, A>(h, h->encoder, enc, x_act, Dp, D, d_enc_out, Z2p, B, st, enc_bias_fused, 0, (spread && gm) ? &wg_enc : nullptr, 1)));
   if (gm) {
     float* dy = h->buf<float>("dy"); A* dlogits_y = h->buf<A>("dlogits_y");
@@ -1232,7 +1335,8 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
       if (!enc_bias_fused) GM_TRY(bias_grad<A>(h, d_prior_out, Z2p, B, 2 * Z, Lp.db, st));
       return 0;
     };
-    if (!spread) GM_TRY(wg_y());
+    if (h->wg_late) h->wg_late->push_back(wg_y);
+    else if (!spread) GM_TRY(wg_y());
     GM_TRY(comm_bucket(h, st, h->bucket_end[1]));   // encoder_gmm and prior_gmm gradients are final
     if (yb_fused) {
       // dlogits_y and encoder_y's last bias gradient were produced by the dy job
@@ -1253,8 +1357,19 @@ static int forward_backward_body(gmvae_handle* h, const uint8_t* x_u8, int B, in
     }
     GM_LAUNCHED(h, st, PC_HEADS);
     }
-    if (spread) GM_TRY(wg_y());                       // filler between the y head and encoder_y's data gradients
+    if (spread && !h->wg_late) GM_TRY(wg_y());        // filler between the y head and encoder_y's data gradients
+    h->part_last_mlp = true;
+    if (h->encoder_y.layers.size() < 2) h->part_tail = true;
     GM_TRY((mlp_backward<A, A>(h, h->encoder_y, ey, x_act, Dp, D, dlogits_y, Kp, B, st, ey_bias_fused)));
+    if (h->wg_late) {                                 // (wg_y captures this scope by reference: run here)
+      h->wg_late = nullptr;
+      for (auto& f : wg_late) GM_TRY(f());
+      wg_late.clear();
+    }
+  }
+  if (h->wg_late) {
+    h->wg_late = nullptr;
+    for (auto& f : wg_late) GM_TRY(f());
   }
   return 0;
 }
@@ -1485,6 +1600,8 @@ int gmvae_create(const gmvae_config* cfg, gmvae_handle** out) {
   const char* dbg = getenv("GMVAE_DEBUG_FLAGS");
   h->debug_flags = dbg ? atoi(dbg) : 0;
   g_use_pdl = !(h->debug_flags & DBG_NO_PDL);
+  if (const char* q = getenv("GMVAE_CHAIN_QUAD")) h->quad_opt_in = atoi(q) != 0;
+  if (const char* q = getenv("GMVAE_CHAIN_SPLIT")) h->chain_split_opt = atoi(q);
   if (const char* bnv = getenv("GMVAE_CHAIN_BN")) { const int v = atoi(bnv); if (v == 128 || v == 192) h->wide_bn = v; }
   plan(h);
   GM_CHECK_CUDA(cudaMalloc(&h->state, sizeof(DeviceState)));

@@ -83,6 +83,12 @@ struct alignas(16) ChainJob {
   ChainDep deps[CHAIN_MAX_DEPS];
   alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
   int rot;                           // 1: the n-tile index is rotated by the row block (see chain_tile)
+  int walk_total;                    // steps of a walker (CTA, CTA pair, 4-CTA cluster) through the job: total_tiles, or tiles_mn2 * num_splits (quad mode)
+  int tiles_mn2;                     // quad mode: double tiles (two adjacent pair tiles) per k-split = ceil(tiles_mn / 2)
+  int wfirst, wcount;                // the walkers [wfirst, wfirst + wcount) take the job's tiles (wcount 0: all of them).  The backward pass
+                                     // gives the chain of dependent data-gradient jobs and the weight-gradient jobs disjoint sets of CTA pairs:
+                                     // an in-order walker cannot step over a long weight-gradient tile to the chain tile queued behind it
+  int share;                         // quad mode: the two pair tiles of a double tile cover the same rows (tiles_n even): A is loaded once, multicast
   int fuse;                          // EK_STORE_F32 jobs with N <= 16: a y head applied to the row in the epilogue (EK_ROWS_Y_FWD / _BWD), 0 = none
   alignas(16) unsigned char epi2[CHAIN_EPI2_BYTES];   // its parameters (RowsYFwd / RowsYBwd)
 };
@@ -140,15 +146,38 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int mn
 // index only -- a quarter of the CTAs all the cheap tiles, the rest all the expensive ones.
 // PAIR: the job's tile space is in PAIR tiles of 256 rows (J.tiles_mn = ceil(row blocks / 2) * tiles_n); CTA `rank` of the pair owns
 // row block 2 * pm + rank (possibly beyond M: a phantom half whose loads read zeros and whose stores are clipped).
-template <bool PAIR>
-__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int rank, int& z, int& mb, int& n0) {
-  z = l / J.tiles_mn;
-  const int mn = l - z * J.tiles_mn;
-  const int pm = mn / J.tiles_n;
+// QUAD (CL = 4): a walker is a cluster of two CTA pairs and `l` counts DOUBLE tiles -- the pair tiles 2d and 2d + 1 of a k-split, taken
+// by pair h = crank >> 1.  With an even number of n-tiles both lie in the same row block: the pairs share the A rows (J.share, TMA
+// multicast).  An odd per-split tile count leaves the last double tile's second half a phantom (rows beyond M).
+template <int CL>
+__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int crank, int& z, int& mb, int& n0) {
+  int mn;
+  if (CL == 4) {
+    z = l / J.tiles_mn2;
+    mn = 2 * (l - z * J.tiles_mn2) + (crank >> 1);
+  } else {
+    z = l / J.tiles_mn;
+    mn = l - z * J.tiles_mn;
+  }
+  int pm = mn / J.tiles_n;
   int nt = mn - pm * J.tiles_n;
+  if (CL == 4 && mn >= J.tiles_mn) { pm = J.tiles_mn / J.tiles_n; nt = 0; }     // phantom pair tile
   if (J.rot) { nt += pm % J.tiles_n; if (nt >= J.tiles_n) nt -= J.tiles_n; }
   n0 = nt * J.block_n;
-  mb = PAIR ? 2 * pm + rank : pm;
+  mb = CL >= 2 ? 2 * pm + (crank & 1) : pm;
+}
+
+// Which tiles of job J walker c (of G) takes: first index and stride; false: none.  MUL: walker units per entry of J.wfirst / J.wcount
+// (row jobs are dealt to single CTAs).
+template <int MUL>
+__device__ __forceinline__ bool chain_walk(const ChainJob& J, int c, int G, int& first, int& stride) {
+  int wf = J.wfirst * MUL, wc = J.wcount * MUL;
+  if (wc <= 0 || wf + wc > G) { wf = 0; wc = G; }          // everybody (also when the grid came out smaller than planned)
+  const int cj = c - wf;
+  if (cj < 0 || cj >= wc) return false;
+  stride = wc;
+  first = ((cj - J.tile_base) % wc + wc) % wc;
+  return true;
 }
 
 struct ChainShared {
@@ -336,18 +365,19 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
 // LSU (measured before: ~16 B/clk/SM, the limiter of the whole step), rows/columns beyond M/N are
 // clipped by the tensor map, and no st.global is issued by the epilogue warps at all.  The ReLU mask
 // source of the backward pass arrives the same way (TMA load of the box into the patch).
-template <class Epi, int KIND, bool PAIR>
+template <class Epi, int KIND, int CL>
 __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUtensorMap* maps, int* counters, const ChainShared& S, int& it,
                                                    uint32_t& op_phase, int warp, int lane, long long* trace, int jidx,
                                                    unsigned long long* jobstat = nullptr, int abl = 0) {
   constexpr int CW = 16;
+  constexpr bool PAIR = CL >= 2;
   Epi epi = *reinterpret_cast<const Epi*>(J.epi);
-  // GEMM tiles are dealt round-robin to the CTAs -- in pair mode to the CTA pairs, both CTAs of a pair walking the same pair tiles
-  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int cidx = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;
-  const int first = ((cidx - J.tile_base) % G + G) % G;
-  if (first >= J.total_tiles) return;
+  // GEMM tiles are dealt round-robin to the walkers (CTAs, CTA pairs or 4-CTA clusters); every CTA of a walker takes the same steps
+  const int G = (int)gridDim.x / CL;
+  const int cidx = (int)blockIdx.x / CL;
+  const int rank = (int)blockIdx.x % CL;                 // place in the cluster
+  int first, wstride;
+  if (!chain_walk<1>(J, cidx, G, first, wstride) || first >= J.walk_total) return;
   const int M = J.M, N = J.N, BN = J.block_n;
   const int nchunk = BN / CW;
   const int e = warp - 2, quad = warp & 3, slot = e >> 2;
@@ -371,9 +401,9 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
       scs_all[i] = 0.f;
     }
   };
-  for (int l = first; l < J.total_tiles; l += G, ++it) {
+  for (int l = first; l < J.walk_total; l += wstride, ++it) {
     int z, mb, n0;
-    chain_tile<PAIR>(J, l, rank, z, mb, n0);
+    chain_tile<CL>(J, l, rank, z, mb, n0);
     const int m0 = mb * BLOCK_M;
     const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
     const int mrow0 = m0 + quad * 32;
@@ -696,13 +726,12 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
 // Data written earlier in this launch by other SMs is read with ld.global.cg (L2), never through L1.
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-template <int KIND, class P>
+template <int KIND, class P, int CL>
 __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters, const ChainShared& S, int warp, int lane,
                                                unsigned long long* jobstat = nullptr, int jidx = 0) {
   const P prm = *reinterpret_cast<const P*>(J.epi);
-  const int G = gridDim.x;
-  const int first = (((int)blockIdx.x - J.tile_base) % G + G) % G;
-  if (first >= J.total_tiles) return;
+  int first, wstride;
+  if (!chain_walk<CL>(J, (int)blockIdx.x, (int)gridDim.x, first, wstride) || first >= J.total_tiles) return;
   const int M = J.M;
   const int et = (int)threadIdx.x - 64;                 // 0 .. 511
   constexpr int NT = EPI_WARPS * 32;
@@ -718,7 +747,7 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
   // A tile is 1/sub of a 128-row block (J.tiles_n = sub): the z heads use 32-row tiles -- one float4 item per epilogue thread -- so
   // that a head stage spreads over every CTA instead of one CTA per row block; every tile signals its block's counter.
   const int sub = J.tiles_n, rpt = BLOCK_M / sub;
-  for (int l = first; l < J.total_tiles; l += G) {
+  for (int l = first; l < J.total_tiles; l += wstride) {
     const int mb = l / sub, m0 = l * rpt;
     const int rows = max(0, min(rpt, M - m0));
     const bool js = jobstat && warp == 2 && lane == 0;
@@ -874,8 +903,13 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
   }
 }
 
-template <class Params, bool PAIR>
+// CL = CTAs per walker: 1 (single CTAs, cta_group::1), 2 (CTA pairs, cta_group::2), 4 (QUAD: clusters of two CTA pairs that take the two
+// n-tiles of a row block together and load its A rows ONCE -- each CTA loads half of its 128 rows and multicasts them to the CTA of the
+// same rank in the other pair.  The operand stream from L2 is what bounds the kernel (profiles/r2_ablation_loads.md): 96 instead of
+// 128 KB per two 256 x 256 x 64 steps).
+template <class Params, int CL>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __grid_constant__ Params p) {
+  constexpr bool PAIR = CL >= 2, QUAD = CL == 4;
   constexpr int STAGES = PAIR ? CHAIN_STAGES_PAIR : CHAIN_STAGES, STAGE_BYTES = PAIR ? CHAIN_STAGE_BYTES_PAIR : CHAIN_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -893,13 +927,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // GEMM tiles: G walkers (CTAs, or CTA pairs), this one is number c; `rank` = this CTA's place in its pair
-  const int G = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x, c = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+  const int G = (int)gridDim.x / CL, c = (int)blockIdx.x / CL;
+  const int crank = (int)blockIdx.x % CL;                   // place in the cluster; pair h = crank >> 1, place in the pair = crank & 1
+  const int rank = crank & 1;
   long long* const trace = (p.trace && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nmaps; ++i) tma_prefetch_desc(&p.maps[i]);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], QUAD ? 2 : 1); }   // quad: a slot is free when BOTH pairs' MMAs have read it (the sibling CTA writes into it)
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&op_bar[s], 1);
     fence_barrier_init();
@@ -909,7 +944,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   if (PAIR) {
-    if (cluster_ctarank() != (uint32_t)rank) __trap();      // the pair must be the two CTAs of one cluster, leader = even block
+    if (cluster_ctarank() != (uint32_t)crank) __trap();     // the pair must be two CTAs of one cluster, leader = even block
     cluster_sync_all();                                       // the peer's barriers exist before anything is signalled on them
   }
   tc_fence_after();
@@ -918,128 +953,162 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
   griddep_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      int pit = 0;
-      for (int j = 0; j < p.njobs; ++j) {
-        const ChainJob& J = p.jobs[j];
-        if (J.kind >= EK_ROWS_FIRST) continue;              // row jobs have no GEMM
-        const int BN = J.block_n, kb1 = J.kb1, kb_total = J.kb1 + J.kb2;
-        // pair mode: this CTA loads its 128 rows of A and HALF of the B tile (K-major: BN/2 rows; MN-major: 64-column slabs)
-        const int bhalf = BN >> 1;
-        const int b_slabs = PAIR ? (bhalf + 63) / 64 : BN / 64;
-        const uint32_t b_bytes = PAIR ? (uint32_t)(J.b_mn ? b_slabs * (BLOCK_K * 128) : bhalf * BLOCK_K * 2) : (uint32_t)(BN * BLOCK_K * 2);
-        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * ((uint32_t)A_STAGE_BYTES + b_bytes);    // pair: both CTAs' loads land on the leader's barrier
-        const int first = ((c - J.tile_base) % G + G) % G;
-        for (int l = first; l < J.total_tiles; l += G, ++pit) {
-          int z, mb, n0;
-          chain_tile<PAIR>(J, l, rank, z, mb, n0);
-          const int m0 = mb * BLOCK_M;
-          const bool real = J.a_mn || m0 < J.M;              // K-major A: rows m0.. exist (a pair's second half may lie beyond M)
-          const int n_eff = min(BN, (J.N - n0 + 15) & ~15);
-          const int nb = PAIR ? n0 + rank * (n_eff >> 1) : n0;  // first B column this CTA loads
-          const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
-          const bool tr = trace && pit < 64;
-          if (tr) trace[16 * pit + 0] = clock64();
-          unsigned long long js_t0 = 0;
-          if (p.jobstat) js_t0 = gtimer();
-          if (J.ndeps > 0) {
-            for (int d = 0; d < J.ndeps; ++d) {
-              const ChainDep& D = J.deps[d];
-              if (D.seg2) continue;
-              if (!D.by_k) {
-                if (real) wait_counter(p.counters + D.base + mb, D.target);
-              } else {
-                const int lo = (kb_begin * BLOCK_K) / BLOCK_M, hi = min(D.nblocks - 1, (kb_end * BLOCK_K - 1) / BLOCK_M);
-                for (int b = lo; b <= hi; ++b) wait_counter(p.counters + D.base + b, D.target);
+    // ===== TMA producer =====
+    // The WHOLE warp walks the schedule with uniform control flow -- loop state, job fields and addresses stay in uniform registers -- and
+    // one elected lane issues the barrier / TMA instructions.  (Run by a single thread inside `if (lane == 0)` the same loop compiled to
+    // ~130 dependent instructions per k-block -- indexed constant loads, R2UR moves and a vote loop around every UTMALDG -- and that
+    // instruction chain, not L2 or the tensor pipe, paced the main loop: profiles/r2_ablation_loads.md.)
+    int stage = 0; uint32_t phase = 0;
+    int pit = 0;
+    for (int j = 0; j < p.njobs; ++j) {
+      const ChainJob& J = p.jobs[j];
+      if (J.kind >= EK_ROWS_FIRST) continue;              // row jobs have no GEMM
+      const int BN = J.block_n, kb1 = J.kb1, kb_total = J.kb1 + J.kb2, a_mn = J.a_mn, b_mn = J.b_mn, ndeps = J.ndeps;
+      const int JM = J.M, JN = J.N, kps = J.kb_per_split, walk_total = J.walk_total, share = J.share;
+      const CUtensorMap* const ta1 = &p.maps[J.a1];
+      const CUtensorMap* const tb1 = &p.maps[J.b1];
+      const CUtensorMap* const ta2 = &p.maps[J.a2];
+      const CUtensorMap* const tb2 = &p.maps[J.b2];
+      // pair mode: this CTA loads its 128 rows of A and HALF of the B tile (K-major: BN/2 rows; MN-major: 64-column slabs)
+      const int bhalf = BN >> 1;
+      const int b_slabs = PAIR ? (bhalf + 63) / 64 : BN / 64;
+      const uint32_t b_bytes = PAIR ? (uint32_t)(b_mn ? b_slabs * (BLOCK_K * 128) : bhalf * BLOCK_K * 2) : (uint32_t)(BN * BLOCK_K * 2);
+      const uint32_t tx_bytes = (PAIR ? 2u : 1u) * ((uint32_t)A_STAGE_BYTES + b_bytes);    // pair: both CTAs' loads land on the leader's barrier
+      bool any_seg2 = false;
+      for (int d = 0; d < ndeps; ++d) any_seg2 = any_seg2 || J.deps[d].seg2 != 0;
+      int first, wstride;
+      if (!chain_walk<1>(J, c, G, first, wstride)) continue;
+      for (int l = first; l < walk_total; l += wstride, ++pit) {
+        int z, mb, n0;
+        chain_tile<CL>(J, l, crank, z, mb, n0);
+        const int m0 = mb * BLOCK_M;
+        const bool real = a_mn || m0 < JM;                 // K-major A: rows m0.. exist (a pair's second half may lie beyond M)
+        const int n_eff = min(BN, (JN - n0 + 15) & ~15);
+        const int nb = PAIR ? n0 + rank * (n_eff >> 1) : n0;  // first B column this CTA loads
+        const int kb_begin = z * kps, kb_end = min(kb_total, kb_begin + kps);
+        const bool tr = trace && pit < 64 && lane == 0;
+        if (tr) trace[16 * pit + 0] = clock64();
+        unsigned long long js_t0 = 0;
+        if (p.jobstat) js_t0 = gtimer();
+        if (ndeps > 0) {
+          for (int d = 0; d < ndeps; ++d) {
+            const ChainDep& D = J.deps[d];
+            if (D.seg2) continue;
+            if (!D.by_k) {
+              if (real) wait_counter(p.counters + D.base + mb, D.target);
+            } else {
+              // every row block of the k-range: one counter per lane, polled in parallel (one thread walking them paid an L2 round
+              // trip per block -- 9 us per weight-gradient tile at cfg4)
+              const int lo = (kb_begin * BLOCK_K) / BLOCK_M, hi = min(D.nblocks - 1, (kb_end * BLOCK_K - 1) / BLOCK_M);
+              for (int b0 = lo; b0 <= hi; b0 += 32) {
+                if (b0 + lane <= hi) wait_counter(p.counters + D.base + b0 + lane, D.target);
+                __syncwarp();
               }
             }
+          }
+          fence_proxy_async_global();                       // (every lane: whichever is elected below has acquired and fenced)
+          __syncwarp();
+        }
+        if (tr) trace[16 * pit + 1] = clock64();
+        if (p.jobstat && lane == 0) { atomicMin(p.jobstat + 8 * j + 0, js_t0); atomicAdd(p.jobstat + 8 * j + 2, gtimer() - js_t0); }
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (kb == kb1 && any_seg2) {
+            // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
+            for (int d = 0; d < ndeps; ++d)
+              if (J.deps[d].seg2 && real) wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target);
             fence_proxy_async_global();
           }
-          if (tr) trace[16 * pit + 1] = clock64();
-          if (p.jobstat) { atomicMin(p.jobstat + 8 * j + 0, js_t0); atomicAdd(p.jobstat + 8 * j + 2, gtimer() - js_t0); }
-          for (int kb = kb_begin; kb < kb_end; ++kb) {
-            if (kb == kb1 && J.ndeps > 0) {
-              // operands of the second K segment may arrive later: the first segment's MMAs run while their producer finishes
-              bool any = false;
-              for (int d = 0; d < J.ndeps; ++d)
-                if (J.deps[d].seg2) { if (real) wait_counter(p.counters + J.deps[d].base + mb, J.deps[d].target); any = true; }
-              if (any) fence_proxy_async_global();
-            }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            const bool seg2 = kb >= kb1;
-            const CUtensorMap* ta = &p.maps[seg2 ? J.a2 : J.a1];
-            const CUtensorMap* tb = &p.maps[seg2 ? J.b2 : J.b1];
-            const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
-            uint8_t* sa = smem + stage * STAGE_BYTES;
-            uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const bool seg2 = kb >= kb1;
+          const CUtensorMap* const ta = seg2 ? ta2 : ta1;
+          const CUtensorMap* const tb = seg2 ? tb2 : tb1;
+          const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
+          uint8_t* const sa = smem + stage * STAGE_BYTES;
+          uint8_t* const sb = sa + A_STAGE_BYTES;
+          uint64_t* const fb = &full_bar[stage];
+          if (elect_one()) {
 #ifdef GMVAE_CHAIN_ABL
             if (p.abl & 2) {
-              if (!PAIR || rank == 0) mbar_arrive(&full_bar[stage]);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              continue;
-            }
+              if (!PAIR || rank == 0) mbar_arrive(fb);
+            } else
 #endif
-            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-            auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
-              if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1); else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
-            };
-            if (J.a_mn) {
+            {
+              if (!PAIR || rank == 0) mbar_expect_tx(fb, tx_bytes);
+              auto ld = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+                if (PAIR) tma_load_2d_pair(m, fb, dst, c0, c1); else tma_load_2d(m, fb, dst, c0, c1);
+              };
+              if (QUAD) {
+                // A in two halves of 64 rows (8 KB; the K-major maps of this mode have 64-row boxes).  Shared rows: this CTA loads half
+                // h and multicasts it to the CTA of the same rank in the other pair, which loads the other half for both.
+                const int hh = crank >> 1;
+                if (share) {
+                  const uint16_t mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+                  if (a_mn) tma_load_2d_pair_mc(ta, fb, sa + hh * 8192, m0 + hh * 64, k_elem, mask);
+                  else tma_load_2d_pair_mc(ta, fb, sa + hh * 8192, k_elem, m0 + hh * 64, mask);
+                } else {
 #pragma unroll
-              for (int i = 0; i < BLOCK_M / 64; ++i) ld(ta, sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
-            } else {
-              ld(ta, sa, k_elem, m0);
+                  for (int i = 0; i < 2; ++i) {
+                    if (a_mn) ld(ta, sa + i * 8192, m0 + i * 64, k_elem); else ld(ta, sa + i * 8192, k_elem, m0 + i * 64);
+                  }
+                }
+              } else if (a_mn) {
+#pragma unroll
+                for (int i = 0; i < BLOCK_M / 64; ++i) ld(ta, sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+              } else {
+                ld(ta, sa, k_elem, m0);
+              }
+              if (b_mn) {
+                for (int i = 0; i < b_slabs; ++i) ld(tb, sb + i * (BLOCK_K * 128), nb + i * 64, k_elem);
+              } else {
+                ld(tb, sb, k_elem, nb);
+              }
             }
-            if (J.b_mn) {
-              for (int i = 0; i < b_slabs; ++i) ld(tb, sb + i * (BLOCK_K * 128), nb + i * 64, k_elem);
-            } else {
-              ld(tb, sb, k_elem, nb);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (tr) trace[16 * pit + 2] = clock64();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tr) trace[16 * pit + 2] = clock64();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread; in pair mode the leader CTA's, for both CTAs) =====
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int j = 0; (!PAIR || rank == 0) && j < p.njobs; ++j) {
-        const ChainJob& J = p.jobs[j];
-        if (J.kind >= EK_ROWS_FIRST) continue;
-        const int kb_total = J.kb1 + J.kb2;
-        const int a_mn = J.a_mn, b_mn = J.b_mn;
-        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-                                ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
-        const uint64_t a_step = a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-        const uint64_t b_step = b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
-        const int first = ((c - J.tile_base) % G + G) % G;
-        for (int l = first; l < J.total_tiles; l += G, ++it) {
-          int z, mb_unused, n0;
-          chain_tile<PAIR>(J, l, 0, z, mb_unused, n0);
-          const int kb_begin = z * J.kb_per_split, kb_end = min(kb_total, kb_begin + J.kb_per_split);
-          const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
-          // a ragged last n-tile runs a narrower MMA (N multiple of 16): the zero-filled columns are not multiplied
-          const int n_eff = min(J.block_n, (J.N - n0 + 15) & ~15);
-          const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
-          const bool tr = trace && it < 64;
-          if (tr) trace[16 * it + 3] = clock64();
-          unsigned long long js_t0 = 0, js_t1 = 0;
-          if (p.jobstat) js_t0 = gtimer();
-          mbar_wait(&tmem_empty_bar[as], ap ^ 1);
+    // ===== MMA issuer (the warp walks the schedule uniformly, one elected lane issues; in pair mode the leader CTA's warp, for both CTAs) =====
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int j = 0; (!PAIR || rank == 0) && j < p.njobs; ++j) {
+      const ChainJob& J = p.jobs[j];
+      if (J.kind >= EK_ROWS_FIRST) continue;
+      const int kb_total = J.kb1 + J.kb2, kps = J.kb_per_split, walk_total = J.walk_total, BN = J.block_n, JN = J.N;
+      const int a_mn = J.a_mn, b_mn = J.b_mn;
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+                              ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
+      const uint64_t a_step = a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint64_t b_step = b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint64_t adesc_hi = make_smem_desc_rt(0, a_mn), bdesc_hi = make_smem_desc_rt(0, b_mn);
+      int first, wstride;
+      if (!chain_walk<1>(J, c, G, first, wstride)) continue;
+      for (int l = first; l < walk_total; l += wstride, ++it) {
+        int z, mb_unused, n0;
+        chain_tile<CL>(J, l, crank, z, mb_unused, n0);
+        const int kb_begin = z * kps, kb_end = min(kb_total, kb_begin + kps);
+        const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+        // a ragged last n-tile runs a narrower MMA (N multiple of 16): the zero-filled columns are not multiplied
+        const int n_eff = min(BN, (JN - n0 + 15) & ~15);
+        const uint32_t idesc = idesc0 | ((uint32_t)(n_eff >> 3) << 17);
+        const bool tr = trace && it < 64 && lane == 0;
+        if (tr) trace[16 * it + 3] = clock64();
+        unsigned long long js_t0 = 0, js_t1 = 0;
+        if (p.jobstat) js_t0 = gtimer();
+        mbar_wait(&tmem_empty_bar[as], ap ^ 1);
+        tc_fence_after();
+        if (p.jobstat) js_t1 = gtimer();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (p.jobstat) js_t1 = gtimer();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
-          for (int kb = kb_begin; kb < kb_end; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (tr && kb == kb_begin) trace[16 * it + 4] = clock64();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint64_t adesc = make_smem_desc_rt(sa, a_mn);
-            const uint64_t bdesc = make_smem_desc_rt(sa + A_STAGE_BYTES, b_mn);
+          if (tr && kb == kb_begin) trace[16 * it + 4] = clock64();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = adesc_hi | (uint64_t)((sa & 0x3FFFF) >> 4);
+          const uint64_t bdesc = bdesc_hi | (uint64_t)(((sa + A_STAGE_BYTES) & 0x3FFFF) >> 4);
+          if (elect_one()) {
 #ifdef GMVAE_CHAIN_ABL
             if (!(p.abl & 4))
 #endif
@@ -1048,13 +1117,17 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
               if (PAIR) umma_bf16_pair(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
               else umma_bf16(adesc + (uint64_t)k * a_step, bdesc + (uint64_t)k * b_step, tmem_d, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             }
-            if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (QUAD) umma_commit_mc(&empty_bar[stage], (uint16_t)0xF);      // the slot is released in all four CTAs
+            else if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
-          if (tr) trace[16 * it + 5] = clock64();
-          if (p.jobstat) { atomicAdd(p.jobstat + 8 * j + 3, gtimer() - js_t1); atomicAdd(p.jobstat + 8 * j + 7, js_t1 - js_t0); }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (elect_one()) {
+          if (QUAD) umma_commit_mc(&tmem_full_bar[as], (uint16_t)(3u << (crank & 2)));
+          else if (PAIR) umma_commit_pair(&tmem_full_bar[as]); else umma_commit(&tmem_full_bar[as]);
+        }
+        if (tr) trace[16 * it + 5] = clock64();
+        if (p.jobstat && lane == 0) { atomicAdd(p.jobstat + 8 * j + 3, gtimer() - js_t1); atomicAdd(p.jobstat + 8 * j + 7, js_t1 - js_t0); }
       }
     }
   } else {
@@ -1065,16 +1138,16 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
     for (int j = 0; j < p.njobs; ++j) {
       const ChainJob& J = p.jobs[j];
       switch (J.kind) {
-        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
-        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
-        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
-        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
-        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, PAIR>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_STORE_BF16: chain_epilogue_job<EpiStore<bf16, EPI_PLAIN>, EK_STORE_BF16, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_STORE_F32: chain_epilogue_job<EpiStore<float, EPI_PLAIN>, EK_STORE_F32, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_BCE: chain_epilogue_job<EpiBCE<bf16>, EK_BCE, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
+        case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
 #ifndef GMVAE_NO_ROWS
-        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
 #endif
         default: break;
       }

@@ -66,6 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a converged warp (the lowest active one; the same lane on every call of a fully active warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -158,6 +165,14 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same, multicast: the box also lands at the same offset in every CTA of `mask` (cluster ranks), each destination's bytes
+// counted on the barrier of ITS pair's leader (quad mode of the chained kernel: the A rows two pairs share)
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -177,6 +192,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint64_t adesc, uint64_t bdesc, u
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 // ---- descriptors ---------------------------------------------------------------------------
@@ -278,74 +298,79 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, int M, int N, int kb1, int
   griddep_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int z = t / tiles_mn, mn = t - z * tiles_mn;
-        const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
-        const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
-        if (trace && blockIdx.x == 0) trace[16 * it + 0] = clock64();
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const bool seg2 = kb >= kb1;
-          const CUtensorMap* ta = seg2 ? &maps.a2 : &maps.a1;
-          const CUtensorMap* tb = seg2 ? &maps.b2 : &maps.b1;
-          const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+    // ===== TMA producer: the whole warp walks the tiles (uniform control flow: loop state and addresses stay in uniform registers),
+    // one elected lane issues.  A single thread inside `if (lane == 0)` compiled to ~130 dependent instructions per k-block (vote
+    // loop around every UTMALDG) and paced the main loop (profiles/r2_ablation_loads.md).
+    const bool tr = trace && blockIdx.x == 0 && lane == 0;
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int z = t / tiles_mn, mn = t - z * tiles_mn;
+      const int m0 = (mn / tiles_n) * BLOCK_M, n0 = (mn % tiles_n) * BLOCK_N;
+      const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      if (tr) trace[16 * it + 0] = clock64();
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const bool seg2 = kb >= kb1;
+        const CUtensorMap* ta = seg2 ? &maps.a2 : &maps.a1;
+        const CUtensorMap* tb = seg2 ? &maps.b2 : &maps.b1;
+        const int k_elem = (seg2 ? kb - kb1 : kb) * BLOCK_K;
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        uint64_t* const fb = &full_bar[stage];
+        if (elect_one()) {
+          mbar_expect_tx(fb, STAGE_BYTES);
           if (A_MN) {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, &full_bar[stage], sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(ta, fb, sa + i * (BLOCK_K * 128), m0 + i * 64, k_elem);
           } else {
-            tma_load_2d(ta, &full_bar[stage], sa, k_elem, m0);
+            tma_load_2d(ta, fb, sa, k_elem, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(tb, &full_bar[stage], sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
+            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(tb, fb, sb + i * (BLOCK_K * 128), n0 + i * 64, k_elem);
           } else {
-            tma_load_2d(tb, &full_bar[stage], sb, k_elem, n0);
+            tma_load_2d(tb, fb, sb, k_elem, n0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (trace && blockIdx.x == 0) trace[16 * it + 1] = clock64();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (tr) trace[16 * it + 1] = clock64();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
-      constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int z = t / tiles_mn;
-        const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
-        const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
-        if (trace && blockIdx.x == 0) trace[16 * it + 2] = clock64();
-        mbar_wait(&tmem_empty_bar[as], ap ^ 1);      // epilogue has drained this accumulator
+    // ===== MMA issuer (the warp walks the tiles uniformly; one elected lane -- the same on every call -- issues and commits) =====
+    constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
+    const bool tr = trace && blockIdx.x == 0 && lane == 0;
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int z = t / tiles_mn;
+      const int kb_begin = z * kb_per_split, kb_end = min(kb_total, kb_begin + kb_per_split);
+      const int as = it & 1; const uint32_t ap = (it >> 1) & 1;
+      if (tr) trace[16 * it + 2] = clock64();
+      mbar_wait(&tmem_empty_bar[as], ap ^ 1);      // epilogue has drained this accumulator
+      tc_fence_after();
+      if (tr) trace[16 * it + 3] = clock64();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (trace && blockIdx.x == 0) trace[16 * it + 3] = clock64();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * ACC_COLS);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (trace && blockIdx.x == 0 && kb == kb_begin) trace[16 * it + 4] = clock64();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc<A_MN>(sa);
-          const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
+        if (tr && kb == kb_begin) trace[16 * it + 4] = clock64();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc<A_MN>(sa);
+        const uint64_t bdesc = make_smem_desc<B_MN>(sa + A_STAGE_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             umma_bf16(adesc + (uint64_t)(k * desc_k_step<A_MN>()), bdesc + (uint64_t)(k * desc_k_step<B_MN>()), tmem_d, idesc,
                       (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[as]);   // accumulator complete
-        if (trace && blockIdx.x == 0) trace[16 * it + 5] = clock64();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[as]);   // accumulator complete
+      if (tr) trace[16 * it + 5] = clock64();
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global =====

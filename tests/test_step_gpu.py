@@ -446,6 +446,40 @@ def test_multi_row_block_ragged_parity(flags, monkeypatch):
         assert v < 3 * TOL["bf16"], (flags, k, v)
 
 
+# Opt-in variants of the one-launch plan (engine.cu): 4-CTA clusters that share the A rows of a row block's two n-tiles by TMA
+# multicast (GMVAE_CHAIN_QUAD=1), the backward pass with the dependent chain and the weight gradients on disjoint CTA pairs
+# (GMVAE_CHAIN_SPLIT=<pairs on the chain>), every weight gradient after the chain (flag 262144).  Slower than the default at cfg4
+#  but kept as measured experiments: they must stay correct.
+@pytest.mark.parametrize("variant", ["quad", "split40", "split12", "wg_late"])
+def test_multi_row_block_variants_parity(variant, monkeypatch):
+    if variant == "quad":
+        monkeypatch.setenv("GMVAE_CHAIN_QUAD", "1")
+    elif variant.startswith("split"):
+        monkeypatch.setenv("GMVAE_CHAIN_SPLIT", variant[5:])
+    else:
+        monkeypatch.setenv("GMVAE_DEBUG_FLAGS", "262144")
+    B = 5000
+    terr, gerr, ref = _parity_at(FULL, "bf16", B)
+    bad = bf16_term_ok(terr, ref, TOL["bf16"])
+    assert not bad, (variant, bad)
+    assert max(gerr.values()) < GRAD_BF16_EXACT, (variant, gerr)
+    _, gerr_model, _ = _parity_at(FULL, "bf16", B, rounding_model=Bf16Model(True))
+    flat = sum(v * v for v in gerr_model.values()) ** 0.5 / len(gerr_model) ** 0.5
+    _record("cfg4_B5000", {"precision": "bf16", "plan": variant, "terms_rel": terr, "grad_vs_exact_max": max(gerr.values()),
+                           "grad_vs_model_max": max(gerr_model.values()), "grad_vs_model_rms": flat})
+    assert flat < 1.5 * TOL["bf16"], (variant, flat)
+    for k, v in gerr_model.items():
+        assert v < 3 * TOL["bf16"], (variant, k, v)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "tiny_gmvae", "k20_ragged", "cfg1"])
+def test_quad_clusters_small_batches(name, monkeypatch):
+    """The 4-CTA cluster form with phantom pair tiles (odd tile counts, one row block) on the forced one-launch plan."""
+    monkeypatch.setenv("GMVAE_CHAIN_QUAD", "1")
+    monkeypatch.setenv("GMVAE_DEBUG_FLAGS", "8192")
+    _check_bf16(name, tag="quad flags=8192")
+
+
 def test_multi_row_block_fp32_mode():
     """fp32 validation mode on 33 row blocks (4 200 rows, ragged): every term and tensor within 1e-5 of the fp64 oracle."""
     terr, gerr, _ = _parity_at(FULL, "fp32", 4200)
