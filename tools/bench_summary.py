@@ -1,3 +1,4 @@
+"""One line per bench.py JSON file: ms per step, the chained kernel's time and fraction of peak.  Usage: python tools/bench_summary.py "glob"."""
 import sys, json, glob
 for f in sorted(glob.glob(sys.argv[1])):
     try:
