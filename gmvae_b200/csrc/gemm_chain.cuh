@@ -113,6 +113,9 @@ typedef ChainParamsT<CHAIN_MAX_JOBS, CHAIN_MAX_MAPS> ChainParams;
 typedef ChainParamsT<CHAIN_SMALL_JOBS, CHAIN_SMALL_MAPS> ChainParamsSmall;
 static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space");
 
+#ifndef GMVAE_POLL_NS
+#define GMVAE_POLL_NS 40          // back-off between two polls of a row-block counter (experiment hook)
+#endif
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -124,12 +127,24 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// Release of a row block: everything this thread wrote (and what the warp's other lanes wrote before the __syncwarp that precedes the
+// call) becomes visible at gpu scope before the counter moves: one release-scoped reduction.  (`legacy`, GMVAE_CHAIN_ABL=8: the form used
+// until late in round 2 -- __threadfence(), i.e. fence.sc.gpu = MEMBAR.SC + L1 invalidate, then a relaxed atomic; 8.7 % of the epilogue
+// warps' stall samples sat on that fence.  Same-box A/B: 0.3593 -> 0.3558 ms per cfg4 step, 2.031 -> 2.011 ms at 131 072 rows.)
+__device__ __forceinline__ void release_counter(int* ctr, int legacy) {
+  if (!legacy) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ctr), "r"(1) : "memory");
+  } else {
+    __threadfence();
+    atomicAdd(ctr, 1);
+  }
+}
 // bounded like mbar_wait: a scheduling bug ends as a trapped launch, not as a hung GPU
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
   if (ld_acquire_gpu(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire_gpu(p) < target) {
-    __nanosleep(40);
+    __nanosleep(GMVAE_POLL_NS);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -689,8 +704,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
       if (J.sig_base >= 0) {
         // rows stored by the bulk copies (async proxy) must be complete and visible before the row block is released
         if constexpr (KIND != EK_STORE_F32) { bulk_wait0(); fence_proxy_async_global(); }
-        __threadfence();
-        atomicAdd(counters + J.sig_base + mb, 1);
+        release_counter(counters + J.sig_base + mb, abl & 8);
       }
     }
     if (tr) trace[16 * it + 10] = clock64();
@@ -728,7 +742,7 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 
 template <int KIND, class P, int CL>
 __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters, const ChainShared& S, int warp, int lane,
-                                               unsigned long long* jobstat = nullptr, int jidx = 0) {
+                                               unsigned long long* jobstat = nullptr, int jidx = 0, int abl = 0) {
   const P prm = *reinterpret_cast<const P*>(J.epi);
   int first, wstride;
   if (!chain_walk<CL>(J, (int)blockIdx.x, (int)gridDim.x, first, wstride) || first >= J.total_tiles) return;
@@ -862,10 +876,7 @@ __device__ __forceinline__ void chain_rows_job(const ChainJob& J, int* counters,
     // release the row block: the rows are read by later jobs through TMA (async proxy) and by plain loads
     fence_proxy_async_global();
     __syncwarp();
-    if (lane == 0 && J.sig_base >= 0) {
-      __threadfence();
-      atomicAdd(counters + J.sig_base + mb, 1);
-    }
+    if (lane == 0 && J.sig_base >= 0) release_counter(counters + J.sig_base + mb, abl & 8);
     if (js) {
       const unsigned long long t2 = gtimer();
       atomicMax(jobstat + 8 * jidx + 1, t2); atomicAdd(jobstat + 8 * jidx + 4, t2 - js_t1); atomicAdd(jobstat + 8 * jidx + 6, 1ull);
@@ -1144,10 +1155,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_chain_kernel(const __gri
         case EK_RELUMASK: chain_epilogue_job<EpiReluMask<bf16, bf16>, EK_RELUMASK, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
         case EK_ATOMIC: chain_epilogue_job<EpiAtomicAdd, EK_ATOMIC, CL>(J, p.maps, p.counters, S, it, op_phase, warp, lane, trace, j, p.jobstat, p.abl); break;
 #ifndef GMVAE_NO_ROWS
-        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
-        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j); break;
+        case EK_ROWS_Y_FWD: chain_rows_job<EK_ROWS_Y_FWD, RowsYFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j, p.abl); break;
+        case EK_ROWS_Z_FWD: chain_rows_job<EK_ROWS_Z_FWD, RowsZFwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j, p.abl); break;
+        case EK_ROWS_Z_BWD: chain_rows_job<EK_ROWS_Z_BWD, RowsZBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j, p.abl); break;
+        case EK_ROWS_Y_BWD: chain_rows_job<EK_ROWS_Y_BWD, RowsYBwd, CL>(J, p.counters, S, warp, lane, p.jobstat, j, p.abl); break;
 #endif
         default: break;
       }
