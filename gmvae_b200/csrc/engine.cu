@@ -542,8 +542,6 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
   static_assert(tc::epi_kind<Epi>::value != tc::EK_NONE, "epilogue not supported by the chained kernel");
   static_assert(sizeof(Epi) <= tc::CHAIN_EPI_BYTES, "epilogue parameters do not fit the job record");
   const bool pair = h->chain_pair, quad = h->chain_quad;
-  const int tiles_m = (M + tc::BLOCK_M - 1) / tc::BLOCK_M, tiles_n = (N + block_n - 1) / block_n;
-  const int tiles_m_walk = pair ? (tiles_m + 1) / 2 : tiles_m;          // pair mode: tiles of 256 rows, one row block per CTA of the pair
   // ---- dependencies
   const void* reads[4] = {A1.ptr, A2 ? A2->ptr : nullptr, a_mn ? (const void*)B1.ptr : nullptr, epi.read_ptr()};
   tc::ChainDep deps[tc::CHAIN_MAX_DEPS]; int ndeps = 0, epi_dep = -1;
@@ -594,14 +592,9 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
     J.a2 = J.a1; J.b2 = J.b1;
   }
   const int kb_total = J.kb1 + J.kb2;
-  if (split_k < 1) split_k = 1;
-  const int per = (kb_total + split_k - 1) / split_k;
-  split_k = (kb_total + per - 1) / per;
-  J.M = M; J.N = N; J.kb_per_split = per; J.num_splits = split_k;
-  J.block_n = block_n; J.a_mn = a_mn ? 1 : 0; J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
-  J.tiles_n = tiles_n; J.tiles_mn = tiles_m_walk * tiles_n; J.total_tiles = J.tiles_mn * split_k; J.tile_base = h->chain_tiles;
-  J.tiles_mn2 = (J.tiles_mn + 1) / 2;
-  J.walk_total = quad ? J.tiles_mn2 * split_k : J.total_tiles;
+  tc::chain_job_geometry(J, M, N, block_n, split_k, kb_total, a_mn, quad ? 4 : pair ? 2 : 1);      // chain_sched.cuh
+  J.b_mn = b_mn ? 1 : 0; J.kind = tc::epi_kind<Epi>::value;
+  J.tile_base = h->chain_tiles;
   {
     const int part = h->part_on ? h->cur_part : 0;
     J.wfirst = part == 2 ? h->part_chain_walkers : 0;
@@ -609,15 +602,13 @@ static int chain_add(gmvae_handle* h, const tc::Operand& A1, const tc::Operand& 
     J.tile_base = part == 0 ? h->chain_tiles : h->part_tiles[part];
     h->part_tiles[part] += J.walk_total;
   }
-  J.share = (quad && tiles_n % 2 == 0) ? 1 : 0;
   J.ndeps = ndeps; J.epi_dep = epi_dep;
-  J.rot = (tiles_n > 1 && N % block_n != 0 && !a_mn) ? 1 : 0;
   for (int d = 0; d < ndeps; ++d) J.deps[d] = deps[d];
   const char *lo, *hi;
   writer_range(epi, M, lo, hi);
   J.sig_base = -1;
   if (lo) {
-    const int ncount = pair ? 2 * tiles_m_walk + (quad ? 2 : 0) : tiles_m;   // (phantom halves / phantom pair tiles signal counters nobody waits for)
+    const int ncount = tc::chain_job_counters(M, quad ? 4 : pair ? 2 : 1);
     if (h->chain_counter_next + ncount <= h->chain_counter_cap) {
       J.sig_base = h->chain_counter_next; h->chain_counter_next += ncount;
     } else {

@@ -20,6 +20,7 @@
 // double-buffered TMEM accumulator, 16 epilogue warps with smem-staged coalesced I/O) are the same.
 #pragma once
 #include "gemm_tc.cuh"
+#include "chain_sched.cuh"
 
 namespace gmvae {
 namespace tc {
@@ -46,9 +47,9 @@ template <> struct epi_kind<EpiAtomicAdd> { static constexpr int value = EK_ATOM
 // warp and 32 columns; read by the data-gradient epilogue with one 4-byte load per row issued ahead of the accumulator) instead of a
 // TMA load of the bf16 activation box in the epilogue's critical path.  Switched per step by the host (engine.cu, DBG_NO_RELU_BITS).
 constexpr bool CHAIN_RELU_BITS = true;
+static_assert(SCHED_BLOCK_M == BLOCK_M, "chain_sched.cuh and gemm_tc.cuh agree on the tile height");
 constexpr int CHAIN_MAX_JOBS = 40;     // a whole forward + backward pass of the 3-MLP model is 33 jobs
 constexpr int CHAIN_MAX_MAPS = 112;    // tensor maps of all jobs (operands, TMA-stored outputs, ReLU-mask sources)
-constexpr int CHAIN_MAX_DEPS = 4;
 constexpr int CHAIN_STAGES = 4;
 constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room for the widest tile (48 KB)
 // CTA-pair mode (cta_group::2, see gemm_tc.cuh): a stage holds this CTA's 128 rows of A and HALF of the B tile's columns
@@ -58,40 +59,11 @@ constexpr int CHAIN_STAGE_BYTES = A_STAGE_BYTES + 256 * BLOCK_K * 2;   // room f
 constexpr int CHAIN_STAGES_PAIR = GMVAE_PAIR_STAGES;
 constexpr int CHAIN_STAGE_BYTES_PAIR = A_STAGE_BYTES + 128 * BLOCK_K * 2;   // 32 KB
 static_assert(CHAIN_STAGES_PAIR * CHAIN_STAGE_BYTES_PAIR <= CHAIN_STAGES * CHAIN_STAGE_BYTES, "both modes use the same ring area");
-constexpr int CHAIN_EPI_BYTES = 128;
-constexpr int CHAIN_EPI2_BYTES = 64;
 constexpr int CHAIN_PATCH_BYTES = 2048;   // per epilogue warp: 32 rows x 64 B, the box of one TMA store (SWIZZLE_64B like the tensor map)
 constexpr int CHAIN_CARVE_BYTES = CHAIN_STAGES * CHAIN_STAGE_BYTES + EPI_WARPS * CHAIN_PATCH_BYTES + 256 /*barriers*/ + 256 * 4 /*bias*/ + 256 * 4 /*column sums*/;
 constexpr int CHAIN_SMEM_BYTES = 232448;  // everything an SM offers one CTA (227 KB); the carve-out needs all but 768 bytes of it
 static_assert(CHAIN_CARVE_BYTES + 512 <= CHAIN_SMEM_BYTES, "shared-memory budget");
 
-// counters[base + row_block] >= target.  by_k = 0: the row block of the consumer's own tile;
-// by_k = 1 (weight gradients: the contraction runs over the batch): every row block its k-range covers.
-struct ChainDep { int base, target, by_k, nblocks, seg2; };   // seg2: only the second K segment reads it (checked when that segment starts)
-
-struct alignas(16) ChainJob {
-  int a1, b1, a2, b2;                // indices into ChainParams::maps
-  int c;                             // epilogue operand read by TMA (ReLU-mask source), box = one patch
-  int d;                             // output written by TMA store / reduce-add, box = one patch
-  int gw;                            // 16-column chunks per 64-byte patch row: 2 (bf16), 1 (fp32), 0: per-row stores
-  int M, N, kb1, kb2, kb_per_split, num_splits;
-  int block_n, a_mn, b_mn, kind;
-  int tiles_n, tiles_mn, total_tiles, tile_base;
-  int sig_base;                      // counters[sig_base + m_block] += 1 per epilogue warp per finished tile; -1: nobody waits
-  int ndeps;
-  int epi_dep;                       // index into deps of the job that wrote the epilogue's own operand (ReLU mask source), or -1
-  ChainDep deps[CHAIN_MAX_DEPS];
-  alignas(16) unsigned char epi[CHAIN_EPI_BYTES];
-  int rot;                           // 1: the n-tile index is rotated by the row block (see chain_tile)
-  int walk_total;                    // steps of a walker (CTA, CTA pair, 4-CTA cluster) through the job: total_tiles, or tiles_mn2 * num_splits (quad mode)
-  int tiles_mn2;                     // quad mode: double tiles (two adjacent pair tiles) per k-split = ceil(tiles_mn / 2)
-  int wfirst, wcount;                // the walkers [wfirst, wfirst + wcount) take the job's tiles (wcount 0: all of them).  The backward pass
-                                     // gives the chain of dependent data-gradient jobs and the weight-gradient jobs disjoint sets of CTA pairs:
-                                     // an in-order walker cannot step over a long weight-gradient tile to the chain tile queued behind it
-  int share;                         // quad mode: the two pair tiles of a double tile cover the same rows (tiles_n even): A is loaded once, multicast
-  int fuse;                          // EK_STORE_F32 jobs with N <= 16: a y head applied to the row in the epilogue (EK_ROWS_Y_FWD / _BWD), 0 = none
-  alignas(16) unsigned char epi2[CHAIN_EPI2_BYTES];   // its parameters (RowsYFwd / RowsYBwd)
-};
 // Passed by value as the kernel's __grid_constant__ parameter.  Two capacities: the recording buffer (a whole
 // forward + backward pass in one launch, about 26 KB of the 32 KB parameter space) and a small one (8 KB) used when
 // the recorded section fits -- the parameter block is copied at every launch, ~3 us for the large one.
@@ -153,46 +125,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int mn
   const uint64_t lbo = mn_major ? (uint64_t)(BLOCK_K * 128) : 0;
   const uint64_t sbo = 1024;
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-// Tile l of a job -> (k-split z, row block mb, first column n0).  n fastest, then m, then k-split.  With J.rot the n-tile index
-// is rotated by the row block: a job whose last n-tile is ragged (784 = 3 x 256 + 16) has cheap and expensive tiles, and since
-// the CTAs walk the tile sequence with a stride (148) that is a multiple of tiles_n, every CTA would otherwise see one n-tile
-// index only -- a quarter of the CTAs all the cheap tiles, the rest all the expensive ones.
-// PAIR: the job's tile space is in PAIR tiles of 256 rows (J.tiles_mn = ceil(row blocks / 2) * tiles_n); CTA `rank` of the pair owns
-// row block 2 * pm + rank (possibly beyond M: a phantom half whose loads read zeros and whose stores are clipped).
-// QUAD (CL = 4): a walker is a cluster of two CTA pairs and `l` counts DOUBLE tiles -- the pair tiles 2d and 2d + 1 of a k-split, taken
-// by pair h = crank >> 1.  With an even number of n-tiles both lie in the same row block: the pairs share the A rows (J.share, TMA
-// multicast).  An odd per-split tile count leaves the last double tile's second half a phantom (rows beyond M).
-template <int CL>
-__device__ __forceinline__ void chain_tile(const ChainJob& J, int l, int crank, int& z, int& mb, int& n0) {
-  int mn;
-  if (CL == 4) {
-    z = l / J.tiles_mn2;
-    mn = 2 * (l - z * J.tiles_mn2) + (crank >> 1);
-  } else {
-    z = l / J.tiles_mn;
-    mn = l - z * J.tiles_mn;
-  }
-  int pm = mn / J.tiles_n;
-  int nt = mn - pm * J.tiles_n;
-  if (CL == 4 && mn >= J.tiles_mn) { pm = J.tiles_mn / J.tiles_n; nt = 0; }     // phantom pair tile
-  if (J.rot) { nt += pm % J.tiles_n; if (nt >= J.tiles_n) nt -= J.tiles_n; }
-  n0 = nt * J.block_n;
-  mb = CL >= 2 ? 2 * pm + (crank & 1) : pm;
-}
-
-// Which tiles of job J walker c (of G) takes: first index and stride; false: none.  MUL: walker units per entry of J.wfirst / J.wcount
-// (row jobs are dealt to single CTAs).
-template <int MUL>
-__device__ __forceinline__ bool chain_walk(const ChainJob& J, int c, int G, int& first, int& stride) {
-  int wf = J.wfirst * MUL, wc = J.wcount * MUL;
-  if (wc <= 0 || wf + wc > G) { wf = 0; wc = G; }          // everybody (also when the grid came out smaller than planned)
-  const int cj = c - wf;
-  if (cj < 0 || cj >= wc) return false;
-  stride = wc;
-  first = ((cj - J.tile_base) % wc + wc) % wc;
-  return true;
 }
 
 struct ChainShared {
