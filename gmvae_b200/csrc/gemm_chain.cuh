@@ -218,11 +218,17 @@ __device__ __forceinline__ void st_row16(float* p, int K, const float* v) {
       if (k < K) p[k] = v[k];
   }
 }
-__device__ __noinline__ float y_head_fwd_row(const float* lg, const RowsYFwd& prm, int64_t row, bool valid) {
+// `noise`: the row's Gumbel noise if the caller has fetched it already (ahead of the accumulator), else nullptr
+__device__ __noinline__ float y_head_fwd_row(const float* lg, const RowsYFwd& prm, int64_t row, bool valid, const float* noise = nullptr) {
   if (!valid) return 0.f;
   const int K = prm.K;
   float a[16];
-  ld_row16(prm.u + row * K, K, a, 0.f);                       // Gumbel noise g = -log(-log u), prepared by the step's first kernel
+  if (noise) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = noise[k];
+  } else {
+    ld_row16(prm.u + row * K, K, a, 0.f);                     // Gumbel noise g = -log(-log u), prepared by the step's first kernel
+  }
   float ml = -INFINITY, ma = -INFINITY;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
@@ -292,13 +298,23 @@ __device__ __noinline__ void y_head_bwd_row(const float* g, const RowsYBwd& prm,
     dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     if (prm.ld_out > 8) dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
   }
+  // Column sums over the warp's 32 rows: a transposing butterfly -- every step halves the values a lane carries while it doubles the
+  // rows they cover (8 + 4 + 2 + 1 + 1 = 16 shuffles; sixteen separate warp sums were 80 and ten serialised shared-memory atomics,
+  // a third of this head's 15 us on the step's critical path).  Lanes 2c and 2c + 1 end up with the sum of column c.
+  const int lane = (int)threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    if (k < K) {                                              // warp-uniform
-      const float t = warp_sum(o[k]);
-      if ((threadIdx.x & 31) == 0 && t != 0.f) atomicAdd(scs + k, t);
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;                        // upper half of the lanes keeps the upper half of the columns
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? o[i] : o[i + w];
+      const float keep = up ? o[i + w] : o[i];
+      o[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
     }
   }
+  const float t = o[0] + __shfl_xor_sync(0xffffffffu, o[0], 1);
+  const int col = lane >> 1;
+  if ((lane & 1) == 0 && col < K && t != 0.f) atomicAdd(scs + col, t);
 }
 
 // The epilogue warps' share of one job.  `it` counts the tiles this CTA has processed since the
@@ -416,6 +432,17 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
       // thin fp32 outputs (logits, [mu|raw], dz, dy) and weight gradients whose row stride is not a
       // multiple of 16 bytes: each lane stores / accumulates its own row fragment
       EpiCtx ctx{nullptr, max(0, min(32, M - mrow0)), sbias, scs_all};
+      float noise[CW];
+      bool have_noise = false;
+      if constexpr (KIND == EK_STORE_F32) {
+        // fused forward y head: the row's Gumbel noise (written by the step's first kernel, complete before this launch reads anything)
+        // is fetched while the accumulator is still being computed
+        if (J.fuse == EK_ROWS_Y_FWD && slot == 0 && mvalid) {
+          const RowsYFwd& yp = *reinterpret_cast<const RowsYFwd*>(J.epi2);
+          ld_row16(yp.u + (int64_t)m * yp.K, yp.K, noise, 0.f);
+          have_noise = true;
+        }
+      }
       wait_acc();
 #pragma unroll 1
       for (int ci = slot; ci < nchunk && n0 + ci * CW < N; ci += 4) {
@@ -442,7 +469,7 @@ __device__ __forceinline__ void chain_epilogue_job(const ChainJob& J, const CUte
                     if (i < N) epi.out[(int64_t)m * epi.ld + i] = lg[i];
                 }
               }
-              fuse_acc += y_head_fwd_row(lg, *reinterpret_cast<const RowsYFwd*>(J.epi2), (int64_t)m, mvalid);
+              fuse_acc += y_head_fwd_row(lg, *reinterpret_cast<const RowsYFwd*>(J.epi2), (int64_t)m, mvalid, have_noise ? noise : nullptr);
             } else {
               y_head_bwd_row(lg, *reinterpret_cast<const RowsYBwd*>(J.epi2), (int64_t)m, mvalid, scs_all);
             }
